@@ -1,0 +1,78 @@
+"""Build recipes: the CUDA C-ABI library (sm_100a only) and the C++ host executable.
+
+Everything is built IN-TREE (xalm_b200/libxalm_cuda.so, xalm_b200/xalm_main) so the artefacts travel to the
+GPU box with the repo snapshot.  nvcc cross-compiles without a GPU.
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libxalm_cuda.so")
+MAIN = os.path.join(HERE, "xalm_main")
+HOSTLIB = os.path.join(HERE, "libxalm_host.so")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+GXX = "/usr/bin/g++"   # the image's $CXX points at a wrapper without OpenMP specs; name the system compiler
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false",
+              "-Xcompiler", "-fPIC", "-ccbin", GXX]
+NVCC_FLAGS = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]
+
+
+def _newer(target: str, sources) -> bool:
+    if not os.path.exists(target):
+        return False
+    t = os.path.getmtime(target)
+    return all(os.path.getmtime(s) <= t for s in sources)
+
+
+def _sources(d, exts):
+    out = []
+    for base, _, files in os.walk(d):
+        for f in files:
+            if f.endswith(exts):
+                out.append(os.path.join(base, f))
+    return out
+
+
+def build_cuda(force: bool = False, verbose: bool = False, extra=()) -> str:
+    deps = _sources(CSRC, (".cu", ".cuh")) + [os.path.join(ROOT, "include", "xalm_cuda.h")]
+    if not force and _newer(LIB, deps):
+        return LIB
+    cmd = [NVCC, *NVCC_FLAGS, *extra, "-shared", "-o", LIB, os.path.join(CSRC, "xalm_cuda.cu"), "-ldl"]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+        print(" ".join(cmd))
+    subprocess.check_call(cmd)
+    return LIB
+
+
+def build_host(force: bool = False) -> str:
+    hdir = os.path.join(CSRC, "host")
+    srcs = [s for s in _sources(hdir, (".cpp",))]
+    if not srcs:
+        return ""
+    deps = srcs + _sources(hdir, (".h",)) + [os.path.join(ROOT, "include", "xalm_cuda.h")]
+    lib_srcs = [s for s in srcs if not s.endswith("main.cpp")]
+    common = [GXX, "-O2", "-std=c++20", "-fPIC", "-fopenmp", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", hdir]
+    if force or not _newer(HOSTLIB, deps):
+        subprocess.check_call([*common, "-shared", "-o", HOSTLIB, *lib_srcs, "-ldl"])
+    main_src = os.path.join(hdir, "main.cpp")
+    if os.path.exists(main_src) and (force or not _newer(MAIN, deps)):
+        subprocess.check_call([*common, "-o", MAIN, main_src, *lib_srcs, "-ldl", f"-Wl,-rpath,{HERE}"])
+    return HOSTLIB
+
+
+def build_all(force: bool = False, verbose: bool = False):
+    build_cuda(force, verbose)
+    build_host(force)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    print("built", LIB)

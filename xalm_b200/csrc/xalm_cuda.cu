@@ -1,0 +1,1162 @@
+// xalm_cuda.cu — implementation of the C ABI in include/xalm_cuda.h: model handle, sharded upload + repack, the
+// per-token kernel sequence (captured once as a CUDA graph with programmatic dependent launches), NCCL plumbing
+// for tensor parallelism, and the op-level entry points the parity tests call.
+//
+// Per token (Model::_forward_cpu, infer.cpp:604-638 / Block::_block_cpu, infer.cpp:365-496):
+//   embed                                   x = dequant(embed[token])
+//   per layer  matvec[norm -> QKV -> rope]  q fp32, k/v fp16 -> KV ring   (+ sink re-rotation)
+//              attn_decode                  xb2 = softmax(q k^T / sqrt(hd)) v      (split-K, GQA)
+//              matvec[Wo, residual]         x += Wo xb2                    (TP: partial -> allreduce -> add)
+//              matvec[norm -> W1|W3 -> GLU] hb = act(W1 xb) * (W3 xb)
+//              matvec[W2, residual]         x += W2 hb                     (TP: partial -> allreduce -> add)
+//   matvec[norm -> classifier]              logits                         (skipped in HYDRATE_KV_CACHE mode)
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <math.h>
+#include <nccl.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "attention.cuh"
+#include "matvec.cuh"
+
+namespace xalm {
+
+thread_local std::string g_last_error;
+
+int set_error(int status, const char* fmt, ...) {
+	char buf[1024];
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(buf, sizeof buf, fmt, ap);
+	va_end(ap);
+	g_last_error = buf;
+	return status;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// tuning knobs (xalm_cuda_tune): integers looked up by name, so GPU sweeps need no recompilation
+// ---------------------------------------------------------------------------------------------------------
+static std::map<std::string, int>& tuning() {
+	static std::map<std::string, int> t = {
+	    {"pdl", 1},          // programmatic dependent launch between the kernels of a token
+	    {"graph", 1},        // replay a captured CUDA graph per token
+	    {"attn_splits", 0},  // 0 = auto (~2 CTAs per SM)
+	    {"attn_min_split", 128},
+	    {"mv_cfg_rows", 0},  // 0 = auto, 1 = force config A (R4 KS1 NW4), 2 = force config B (R2 KS4 NW8)
+	};
+	return t;
+}
+static int tune(const char* k) {
+	const char* e = nullptr;
+	std::string env = std::string("XALM_") + k;
+	for (auto& ch : env) ch = (char) toupper(ch);
+	if ((e = getenv(env.c_str()))) return atoi(e);
+	return tuning()[k];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// launch helper (optionally with the programmatic-stream-serialisation attribute = PDL)
+// ---------------------------------------------------------------------------------------------------------
+template <typename... KArgs, typename... Args>
+static cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, bool pdl, Args&&... args) {
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = grid;
+	cfg.blockDim = block;
+	cfg.dynamicSmemBytes = 0;
+	cfg.stream = stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+	cfg.attrs = attr;
+	cfg.numAttrs = 1;
+	return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// matvec dispatch
+// ---------------------------------------------------------------------------------------------------------
+struct MvCfg {
+	int R, KS, NW;
+};
+static const MvCfg CFG_A = {4, 1, 4}; // many rows: 16 virtual rows per 128-thread CTA
+static const MvCfg CFG_B = {2, 4, 8}; // few rows (Wo, W2): 4 rows per CTA, K split over 4 warps
+
+template <int TYPE>
+static cudaError_t launch_matvec_typed(const MatvecArgs& a, const MvCfg& c, bool norm, cudaStream_t s, bool pdl) {
+	const int vrows = a.epi == EPI_GLU ? 2 * a.d : a.d;
+	if (c.KS == 1) {
+		const int rows_per_cta = (CFG_A.NW / CFG_A.KS) * CFG_A.R;
+		dim3 grid((vrows + rows_per_cta - 1) / rows_per_cta), block(CFG_A.NW * 32);
+		if (norm) return launch(matvec_kernel<TYPE, 4, 1, 4, true>, grid, block, s, pdl, a);
+		return launch(matvec_kernel<TYPE, 4, 1, 4, false>, grid, block, s, pdl, a);
+	}
+	const int rows_per_cta = (CFG_B.NW / CFG_B.KS) * CFG_B.R;
+	dim3 grid((vrows + rows_per_cta - 1) / rows_per_cta), block(CFG_B.NW * 32);
+	if (norm) return launch(matvec_kernel<TYPE, 2, 4, 8, true>, grid, block, s, pdl, a);
+	return launch(matvec_kernel<TYPE, 2, 4, 8, false>, grid, block, s, pdl, a);
+}
+
+static int launch_matvec(MatvecArgs a, cudaStream_t s, bool pdl) {
+	const bool norm = a.norm_w != nullptr;
+	if (norm && a.norm_type != XALM_F32 && a.norm_type != XALM_BF16)
+		return set_error(XALM_ERR_UNSUPPORTED, "rmsnorm: unsupported data type %d", a.norm_type); // infer.cpp:248-249
+	if (a.n % 32 || (a.epi != EPI_GLU && a.d % 2))
+		return set_error(XALM_ERR_INVALID, "matmul: n=%d d=%d must be multiples of 32", a.n, a.d); // infer.cpp:110-111
+	const int vrows = a.epi == EPI_GLU ? 2 * a.d : a.d;
+	int t = a.w.type;
+	cudaError_t e;
+	if (t == XALM_TQ1_0) {
+		if (a.n % 256) return set_error(XALM_ERR_INVALID, "TQ1_0 rows must be a multiple of 256 elements (n=%d)", a.n);
+		dim3 grid((vrows + 4 * 4 - 1) / (4 * 4)), block(4 * 32);
+		e = norm ? launch(matvec_tq1_kernel<4, 4, true>, grid, block, s, pdl, a)
+		         : launch(matvec_tq1_kernel<4, 4, false>, grid, block, s, pdl, a);
+		if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "matvec launch failed: %s", cudaGetErrorString(e));
+		return XALM_OK;
+	}
+	// config: enough CTAs to cover 148 SMs several times over with balanced shares
+	MvCfg c = vrows >= 6144 ? CFG_A : CFG_B;
+	const int force = tune("mv_cfg_rows");
+	if (force == 1) c = CFG_A;
+	if (force == 2) c = CFG_B;
+	a.lut_type = 0;
+	if (t == XALM_F8_E2M5 || t == XALM_F8_E3M4 || t == XALM_QI8 ||
+	    ((t == XALM_F8_E4M3 || t == XALM_F8_E5M2) && (a.w.flags & WMAT_FP8_NONFINITE))) {
+		a.lut_type = t;
+		t = -1;
+	}
+	switch (t) {
+		case -1: e = launch_matvec_typed<-1>(a, c, norm, s, pdl); break;
+		case XALM_F32: e = launch_matvec_typed<XALM_F32>(a, c, norm, s, pdl); break;
+		case XALM_F16: e = launch_matvec_typed<XALM_F16>(a, c, norm, s, pdl); break;
+		case XALM_BF16: e = launch_matvec_typed<XALM_BF16>(a, c, norm, s, pdl); break;
+		case XALM_F8_E4M3: e = launch_matvec_typed<XALM_F8_E4M3>(a, c, norm, s, pdl); break;
+		case XALM_F8_E5M2: e = launch_matvec_typed<XALM_F8_E5M2>(a, c, norm, s, pdl); break;
+		case XALM_Q8: e = launch_matvec_typed<XALM_Q8>(a, c, norm, s, pdl); break;
+		case XALM_Q8_0: e = launch_matvec_typed<XALM_Q8_0>(a, c, norm, s, pdl); break;
+		case XALM_Q4_0: e = launch_matvec_typed<XALM_Q4_0>(a, c, norm, s, pdl); break;
+		case XALM_Q4_1: e = launch_matvec_typed<XALM_Q4_1>(a, c, norm, s, pdl); break;
+		case XALM_Q5_0: e = launch_matvec_typed<XALM_Q5_0>(a, c, norm, s, pdl); break;
+		case XALM_Q5_1: e = launch_matvec_typed<XALM_Q5_1>(a, c, norm, s, pdl); break;
+		default:
+			return set_error(XALM_ERR_UNSUPPORTED, "matmul: unsupported data type: %d", a.w.type); // infer.cpp:211-214
+	}
+	if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "matvec launch failed: %s", cudaGetErrorString(e));
+	return XALM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------------------------------------
+// _copy_embedding (infer.cpp:553-602) from the ON-DISK layout of the table (block formats: extension)
+__global__ void embed_kernel(int type, const uint8_t* __restrict__ table, size_t row_bytes, int dim, const StepParams* step,
+                             float* __restrict__ x) {
+	pdl_launch_dependents();
+	pdl_wait();
+	const uint8_t* row = table + (size_t) step->token * row_bytes;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += gridDim.x * blockDim.x) x[i] = decode_disk_elem(type, row, i);
+}
+
+__global__ void dequant_kernel(int type, const uint8_t* __restrict__ src, size_t n, float* __restrict__ dst) {
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+		dst[i] = decode_disk_elem(type, src, i);
+}
+
+__global__ void residual_add_kernel(float* __restrict__ x, const float* __restrict__ y, int n) {
+	pdl_launch_dependents();
+	pdl_wait();
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] += y[i];
+}
+
+// standalone rmsnorm / rope for the op-level entry points (the hot path fuses both into the matvec kernel)
+__global__ void rmsnorm_kernel(float* o, const float* x, const uint8_t* w, int wtype, int size, float eps) {
+	__shared__ float s_red[32];
+	float ss = 0.f;
+	for (int i = threadIdx.x; i < size; i += blockDim.x) ss += x[i] * x[i];
+	ss = warp_sum(ss);
+	if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = ss;
+	__syncthreads();
+	float tot = 0.f;
+	for (int i = 0; i < (int) (blockDim.x + 31) / 32; i++) tot += s_red[i];
+	const float scale = 1.0f / sqrtf(tot / (float) size + eps);
+	for (int i = threadIdx.x; i < size; i += blockDim.x) {
+		const float g = wtype == XALM_F32 ? reinterpret_cast<const float*>(w)[i] : bf16_bits_to_f32(reinterpret_cast<const uint16_t*>(w)[i]);
+		o[i] = x[i] * scale * g;
+	}
+}
+__global__ void rope_kernel(float* vec, int d, int head_dim, int pos, const float* freq) {
+	for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < d / 2; p += gridDim.x * blockDim.x) {
+		float v0 = vec[2 * p], v1 = vec[2 * p + 1];
+		rope_pair(v0, v1, (2 * p) % head_dim, pos, freq);
+		vec[2 * p] = v0;
+		vec[2 * p + 1] = v1;
+	}
+}
+
+// 1/powf(theta, j/rotary_dim) on the HOST, exactly the expression of infer.cpp:310-312 (0 beyond rotary_dim)
+static std::vector<float> rope_freq_table(int head_dim, int rotary_dim, float theta) {
+	std::vector<float> f(head_dim / 2);
+	for (int j = 0; j < head_dim; j += 2)
+		f[j / 2] = j >= rotary_dim ? 0.f : 1.0f / powf(theta, (float) j / (float) rotary_dim);
+	return f;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// attention dispatch
+// ---------------------------------------------------------------------------------------------------------
+template <int HD>
+static cudaError_t launch_attn_hd(const AttnArgs& a, int G, cudaStream_t s, bool pdl) {
+	dim3 grid(a.n_splits, a.n_kv_heads), block(128);
+	switch (G) {
+		case 1: return launch(attn_decode_kernel<HD, 1, 4>, grid, block, s, pdl, a);
+		case 2: return launch(attn_decode_kernel<HD, 2, 4>, grid, block, s, pdl, a);
+		case 4: return launch(attn_decode_kernel<HD, 4, 4>, grid, block, s, pdl, a);
+		case 8: return launch(attn_decode_kernel<HD, 8, 4>, grid, block, s, pdl, a);
+	}
+	return cudaErrorInvalidValue;
+}
+static int launch_attn(const AttnArgs& a, int head_dim, int G, cudaStream_t s, bool pdl) {
+	cudaError_t e;
+	switch (head_dim) {
+		case 32: e = launch_attn_hd<32>(a, G, s, pdl); break;
+		case 64: e = launch_attn_hd<64>(a, G, s, pdl); break;
+		case 128: e = launch_attn_hd<128>(a, G, s, pdl); break;
+		case 256: e = launch_attn_hd<256>(a, G, s, pdl); break;
+		default: return set_error(XALM_ERR_UNSUPPORTED, "attention: head_dim %d not in {32,64,128,256}", head_dim);
+	}
+	if (e == cudaErrorInvalidValue && (G != 1 && G != 2 && G != 4 && G != 8))
+		return set_error(XALM_ERR_UNSUPPORTED, "attention: %d query heads per kv head not in {1,2,4,8}", G);
+	if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "attention launch failed: %s", cudaGetErrorString(e));
+	return XALM_OK;
+}
+static int attn_auto_splits(int n_kv_heads) {
+	int forced = tune("attn_splits");
+	if (forced > 0) return forced;
+	int sms = 148;
+	int dev = 0;
+	if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	int s = (2 * sms + n_kv_heads - 1) / n_kv_heads;
+	return s < 1 ? 1 : s;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// device weight storage
+// ---------------------------------------------------------------------------------------------------------
+struct DevAlloc {
+	std::vector<void*> ptrs;
+	size_t total = 0;
+	int alloc(void** p, size_t bytes) {
+		if (bytes == 0) bytes = 16;
+		cudaError_t e = cudaMalloc(p, bytes);
+		if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+		ptrs.push_back(*p);
+		total += bytes;
+		return XALM_OK;
+	}
+	void free_all() {
+		for (void* p : ptrs) cudaFree(p);
+		ptrs.clear();
+	}
+};
+
+// A weight matrix being assembled from one or more uploaded pieces stacked along rows (q|k|v, gate|up).
+struct WSlot {
+	WMat m;            // planes for ALL rows of the fused matrix
+	int total_rows = 0;
+	bool allocated = false;
+};
+
+static int alloc_wmat(DevAlloc& da, WMat& m, int type, int rows, int n) {
+	const PlaneSizes ps = plane_row_bytes(type, n);
+	m.type = type; m.rows = rows; m.n = n; m.flags = 0;
+	m.s0 = ps.s0; m.s1 = ps.s1; m.s2 = ps.s2;
+	uint8_t *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;
+	XALM_TRY(da.alloc((void**) &p0, ps.s0 * rows));
+	if (ps.s1) XALM_TRY(da.alloc((void**) &p1, ps.s1 * rows));
+	if (ps.s2) XALM_TRY(da.alloc((void**) &p2, ps.s2 * rows));
+	m.p0 = p0; m.p1 = p1; m.p2 = p2;
+	return XALM_OK;
+}
+
+// Copy rows [r0,r1) x element columns [c0,c1) of a host tensor (on-disk layout, `n_full` elements per row) to the
+// device and repack them into rows [dst_row, ...) of `m`.  `staging` is a reusable device scratch buffer.
+struct Staging {
+	uint8_t* p = nullptr;
+	size_t cap = 0;
+	int* flag = nullptr;
+};
+static int upload_piece(WMat& m, int dst_row, int type, const uint8_t* host, int n_full, int r0, int r1, int c0, int c1,
+                        Staging& st, cudaStream_t s) {
+	TypeInfo ti;
+	type_info(type, &ti);
+	if (n_full % ti.block || c0 % ti.block || c1 % ti.block)
+		return set_error(XALM_ERR_INVALID, "column range [%d,%d) of %d splits a %d-element block", c0, c1, n_full, ti.block);
+	const size_t full_row = (size_t) n_full / ti.block * ti.bytes;
+	const size_t width = (size_t) (c1 - c0) / ti.block * ti.bytes;
+	const size_t off = (size_t) c0 / ti.block * ti.bytes;
+	const int rows = r1 - r0;
+	const size_t need = width * rows;
+	if (need > st.cap) {
+		if (st.p) cudaFree(st.p);
+		st.p = nullptr; st.cap = 0;
+		XALM_CUDA_CHECK(cudaMalloc((void**) &st.p, need));
+		st.cap = need;
+	}
+	if (!st.flag) XALM_CUDA_CHECK(cudaMalloc((void**) &st.flag, sizeof(int)));
+	XALM_CUDA_CHECK(cudaMemcpy2DAsync(st.p, width, host + (size_t) r0 * full_row + off, full_row, width, rows, cudaMemcpyHostToDevice, s));
+	const int n = c1 - c0;
+	uint8_t* p0 = const_cast<uint8_t*>(m.p0) + (size_t) dst_row * m.s0;
+	uint8_t* p1 = m.p1 ? const_cast<uint8_t*>(m.p1) + (size_t) dst_row * m.s1 : nullptr;
+	uint8_t* p2 = m.p2 ? const_cast<uint8_t*>(m.p2) + (size_t) dst_row * m.s2 : nullptr;
+	repack_kernel<<<1024, 256, 0, s>>>(type, st.p, width, rows, n, p0, m.s0, p1, m.s1, p2, m.s2);
+	XALM_CUDA_CHECK(cudaGetLastError());
+	if (type == XALM_F8_E4M3 || type == XALM_F8_E5M2) {
+		XALM_CUDA_CHECK(cudaMemsetAsync(st.flag, 0, sizeof(int), s));
+		fp8_scan_nonfinite_kernel<<<256, 256, 0, s>>>(type, st.p, need, st.flag);
+		int h = 0;
+		XALM_CUDA_CHECK(cudaMemcpyAsync(&h, st.flag, sizeof(int), cudaMemcpyDeviceToHost, s));
+		XALM_CUDA_CHECK(cudaStreamSynchronize(s));
+		if (h) m.flags |= WMAT_FP8_NONFINITE;
+	}
+	XALM_CUDA_CHECK(cudaStreamSynchronize(s));
+	return XALM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// NCCL, loaded lazily: single-GPU users need no libnccl at all, and inside a torch process the already-loaded
+// libnccl.so.2 is the one dlopen returns.
+// ---------------------------------------------------------------------------------------------------------
+struct NcclApi {
+	void* h = nullptr;
+	ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+	ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+	ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+	const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi g_nccl;
+static int nccl_load() {
+	if (g_nccl.h) return XALM_OK;
+	const char* names[] = {"libnccl.so.2", "libnccl.so"};
+	for (const char* n : names)
+		if ((g_nccl.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+	if (!g_nccl.h) return set_error(XALM_ERR_COMM, "cannot load libnccl: %s", dlerror());
+#define XALM_NCCL_SYM(field, sym)                                                                      \
+	if (!(*(void**) (&g_nccl.field) = dlsym(g_nccl.h, sym))) {                                         \
+		g_nccl.h = nullptr;                                                                            \
+		return set_error(XALM_ERR_COMM, "libnccl lacks %s", sym);                                      \
+	}
+	XALM_NCCL_SYM(GetUniqueId, "ncclGetUniqueId");
+	XALM_NCCL_SYM(CommInitRank, "ncclCommInitRank");
+	XALM_NCCL_SYM(AllReduce, "ncclAllReduce");
+	XALM_NCCL_SYM(AllGather, "ncclAllGather");
+	XALM_NCCL_SYM(CommDestroy, "ncclCommDestroy");
+	XALM_NCCL_SYM(GetErrorString, "ncclGetErrorString");
+#undef XALM_NCCL_SYM
+	return XALM_OK;
+}
+#define XALM_NCCL_CHECK(expr)                                                                                     \
+	do {                                                                                                          \
+		ncclResult_t _r = (expr);                                                                                 \
+		if (_r != ncclSuccess) return set_error(XALM_ERR_COMM, "%s failed: %s", #expr, g_nccl.GetErrorString(_r)); \
+	} while (0)
+
+} // namespace xalm
+
+using namespace xalm;
+
+// ---------------------------------------------------------------------------------------------------------
+// the model handle
+// ---------------------------------------------------------------------------------------------------------
+struct LayerDev {
+	WSlot wqkv, wo, w13, w2;
+	const uint8_t* rms_att = nullptr;
+	const uint8_t* rms_ffn = nullptr;
+	int rms_att_type = 0, rms_ffn_type = 0;
+	__half* k_cache = nullptr;
+	__half* v_cache = nullptr;
+	bool got[9] = {false, false, false, false, false, false, false, false, false};
+	int piece_type[9] = {0};
+};
+enum { P_ATT_NORM = 0, P_FFN_NORM, P_Q, P_K, P_V, P_O, P_GATE, P_DOWN, P_UP };
+
+struct xalm_cuda_model {
+	xalm_config c;
+	int device = 0, tp_rank = 0, tp_size = 1;
+	// local (per-rank) sizes
+	int q_dim = 0, kv_dim = 0, q_dim_l = 0, kv_dim_l = 0, n_heads_l = 0, n_kv_heads_l = 0, hidden_l = 0, vocab_l = 0;
+	DevAlloc da;
+	Staging staging;
+	// weights
+	uint8_t* embed_raw = nullptr; // on-disk layout, all rows (replicated)
+	int embed_type = 0;
+	size_t embed_row_bytes = 0;
+	bool got_embed = false, got_final_norm = false, got_cls = false;
+	WSlot wcls;
+	const uint8_t* rms_final = nullptr;
+	int rms_final_type = 0;
+	std::vector<LayerDev> layers;
+	// state (InferenceState, model.h:96-156 — only what the fused kernels still materialise)
+	float *x = nullptr, *xb2 = nullptr, *hb = nullptr, *q = nullptr, *logits = nullptr, *logits_full = nullptr, *part = nullptr;
+	float* rope_freq = nullptr;
+	float *attn_acc = nullptr, *attn_ml = nullptr;
+	unsigned int* tickets = nullptr;
+	int attn_splits = 0;
+	StepParams* d_step = nullptr;
+	StepParams* h_step = nullptr; // pinned ring
+	cudaEvent_t h_step_ev[64];
+	bool h_step_ev_used[64];
+	int step_slot = 0;
+	float* h_logits = nullptr; // pinned
+	cudaStream_t own_stream = nullptr, stream = nullptr;
+	cudaGraphExec_t graph[2] = {nullptr, nullptr};
+	bool finalized = false;
+	int launches_per_token[2] = {0, 0};
+	int last_launches = 0;
+	ncclComm_t comm = nullptr;
+};
+
+static int parse_tensor_name(const char* name, int n_layers, int* layer, int* piece) {
+	// model.cpp:83-114
+	*layer = -1;
+	*piece = -1;
+	if (!strcmp(name, "embed.weight")) { *piece = 100; return XALM_OK; }
+	if (!strcmp(name, "output.norm.weight")) { *piece = 101; return XALM_OK; }
+	if (!strcmp(name, "output.weight")) { *piece = 102; return XALM_OK; }
+	int l = -1;
+	char rest[64] = {0};
+	if (sscanf(name, "l.%d.%63s", &l, rest) == 2 && l >= 0 && l < n_layers) {
+		static const char* names[9] = {"attn.norm.weight", "mlp.norm.weight", "attn.q.weight", "attn.k.weight", "attn.v.weight",
+		                               "attn.down.weight", "mlp.gate.weight", "mlp.down.weight", "mlp.up.weight"};
+		for (int i = 0; i < 9; i++)
+			if (!strcmp(rest, names[i])) { *layer = l; *piece = i; return XALM_OK; }
+	}
+	return set_error(XALM_ERR_INVALID, "unknown tensor name '%s'", name);
+}
+
+extern "C" {
+
+int xalm_cuda_abi_version(void) { return XALM_CUDA_ABI_VERSION; }
+const char* xalm_cuda_last_error(void) { return g_last_error.c_str(); }
+
+int xalm_cuda_device_count(int* count) {
+	if (!count) return set_error(XALM_ERR_INVALID, "count is NULL");
+	XALM_CUDA_CHECK(cudaGetDeviceCount(count));
+	return XALM_OK;
+}
+
+int xalm_cuda_type_info(int type_id, int* block_elems, int* block_bytes) {
+	TypeInfo ti;
+	if (!type_info(type_id, &ti)) return set_error(XALM_ERR_INVALID, "invalid type: %d", type_id);
+	if (block_elems) *block_elems = ti.block;
+	if (block_bytes) *block_bytes = ti.bytes;
+	return XALM_OK;
+}
+
+int xalm_cuda_tune(const char* key, int value) {
+	if (!key || !tuning().count(key)) return set_error(XALM_ERR_INVALID, "unknown tuning key '%s'", key ? key : "(null)");
+	tuning()[key] = value;
+	return XALM_OK;
+}
+
+int xalm_cuda_create(const xalm_config* cfg, int device, int tp_rank, int tp_size, xalm_cuda_model** out) {
+	if (!cfg || !out) return set_error(XALM_ERR_INVALID, "cfg/out is NULL");
+	*out = nullptr;
+	const xalm_config& c = *cfg;
+	if (c.dim <= 0 || c.hidden_dim <= 0 || c.head_dim <= 0 || c.n_layers <= 0 || c.n_heads <= 0 || c.n_kv_heads <= 0 ||
+	    c.vocab_size <= 0 || c.max_seq_len <= 0)
+		return set_error(XALM_ERR_INVALID, "config has a non-positive dimension");
+	if (c.n_heads % c.n_kv_heads) return set_error(XALM_ERR_INVALID, "n_heads %d not a multiple of n_kv_heads %d", c.n_heads, c.n_kv_heads);
+	if (c.dim % 32 || c.hidden_dim % 32 || c.vocab_size % 32 || (c.n_heads * c.head_dim) % 32 || (c.n_kv_heads * c.head_dim) % 32)
+		return set_error(XALM_ERR_INVALID, "matmul dimensions must be multiples of 32 (infer.cpp:110-111)");
+	if (c.head_dim % 2 || c.rotary_dim > c.head_dim || c.rotary_dim < 0) return set_error(XALM_ERR_INVALID, "bad head_dim/rotary_dim");
+	if (c.max_seq_len <= 2) return set_error(XALM_ERR_INVALID, "max_seq_len must exceed KV_SINKS (2)");
+	if (c.norm_type != 0) return set_error(XALM_ERR_UNSUPPORTED, "unsupported norm type");
+	if (c.act != XALM_GELU && c.act != XALM_SILU) return set_error(XALM_ERR_UNSUPPORTED, "unsupported activation type");
+	if (tp_size < 1 || tp_rank < 0 || tp_rank >= tp_size) return set_error(XALM_ERR_INVALID, "bad tp_rank/tp_size %d/%d", tp_rank, tp_size);
+	if (c.n_kv_heads % tp_size || c.n_heads % tp_size || c.hidden_dim % (32 * tp_size) || c.vocab_size % (32 * tp_size) ||
+	    ((c.n_heads / tp_size) * c.head_dim) % 32)
+		return set_error(XALM_ERR_INVALID, "tp_size %d does not divide heads/hidden/vocab into 32-aligned shards", tp_size);
+	int ndev = 0;
+	XALM_CUDA_CHECK(cudaGetDeviceCount(&ndev));
+	if (device < 0 || device >= ndev) return set_error(XALM_ERR_CUDA, "device %d not available (%d devices)", device, ndev);
+	XALM_CUDA_CHECK(cudaSetDevice(device));
+	xalm_cuda_model* m = new xalm_cuda_model();
+	m->c = c;
+	m->device = device; m->tp_rank = tp_rank; m->tp_size = tp_size;
+	m->q_dim = c.n_heads * c.head_dim;
+	m->kv_dim = c.n_kv_heads * c.head_dim;
+	m->n_heads_l = c.n_heads / tp_size;
+	m->n_kv_heads_l = c.n_kv_heads / tp_size;
+	m->q_dim_l = m->n_heads_l * c.head_dim;
+	m->kv_dim_l = m->n_kv_heads_l * c.head_dim;
+	m->hidden_l = c.hidden_dim / tp_size;
+	m->vocab_l = c.vocab_size / tp_size;
+	m->layers.resize(c.n_layers);
+	memset(m->h_step_ev_used, 0, sizeof m->h_step_ev_used);
+	cudaError_t e = cudaStreamCreateWithFlags(&m->own_stream, cudaStreamNonBlocking);
+	if (e != cudaSuccess) { delete m; return set_error(XALM_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e)); }
+	m->stream = m->own_stream;
+	*out = m;
+	return XALM_OK;
+}
+
+void xalm_cuda_destroy(xalm_cuda_model* m) {
+	if (!m) return;
+	cudaSetDevice(m->device);
+	cudaStreamSynchronize(m->stream);
+	for (int i = 0; i < 2; i++)
+		if (m->graph[i]) cudaGraphExecDestroy(m->graph[i]);
+	if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
+	for (int i = 0; i < 64; i++)
+		if (m->h_step_ev_used[i]) cudaEventDestroy(m->h_step_ev[i]);
+	m->da.free_all();
+	if (m->staging.p) cudaFree(m->staging.p);
+	if (m->staging.flag) cudaFree(m->staging.flag);
+	if (m->h_step) cudaFreeHost(m->h_step);
+	if (m->h_logits) cudaFreeHost(m->h_logits);
+	if (m->own_stream) cudaStreamDestroy(m->own_stream);
+	delete m;
+}
+
+int xalm_cuda_set_stream(xalm_cuda_model* m, void* cuda_stream) {
+	if (!m) return set_error(XALM_ERR_INVALID, "model is NULL");
+	m->stream = cuda_stream ? (cudaStream_t) cuda_stream : m->own_stream;
+	return XALM_OK;
+}
+
+int xalm_cuda_comm_unique_id(void* id128) {
+	if (!id128) return set_error(XALM_ERR_INVALID, "id is NULL");
+	XALM_TRY(nccl_load());
+	static_assert(sizeof(ncclUniqueId) == XALM_COMM_ID_BYTES, "ncclUniqueId size");
+	ncclUniqueId id;
+	XALM_NCCL_CHECK(g_nccl.GetUniqueId(&id));
+	memcpy(id128, &id, sizeof id);
+	return XALM_OK;
+}
+
+int xalm_cuda_comm_init(xalm_cuda_model* m, const void* id128) {
+	if (!m || !id128) return set_error(XALM_ERR_INVALID, "model/id is NULL");
+	if (m->tp_size == 1) return XALM_OK;
+	if (m->finalized) return set_error(XALM_ERR_STATE, "comm_init must precede finalize");
+	XALM_TRY(nccl_load());
+	XALM_CUDA_CHECK(cudaSetDevice(m->device));
+	ncclUniqueId id;
+	memcpy(&id, id128, sizeof id);
+	XALM_NCCL_CHECK(g_nccl.CommInitRank(&m->comm, m->tp_size, id, m->tp_rank));
+	return XALM_OK;
+}
+
+int xalm_cuda_upload_tensor(xalm_cuda_model* m, const char* name, int type_id, const int* shape, int rank, const void* data,
+                            size_t nbytes) {
+	if (!m || !name || !shape || !data) return set_error(XALM_ERR_INVALID, "NULL argument");
+	if (m->finalized) return set_error(XALM_ERR_STATE, "upload after finalize");
+	XALM_CUDA_CHECK(cudaSetDevice(m->device));
+	const xalm_config& c = m->c;
+	int layer, piece;
+	XALM_TRY(parse_tensor_name(name, c.n_layers, &layer, &piece));
+	TypeInfo ti;
+	if (!type_info(type_id, &ti)) return set_error(XALM_ERR_INVALID, "invalid type: %d", type_id);
+	// expected element shapes: model.cpp:83-114
+	int er = 0, ec = 0;
+	bool is_norm = false;
+	switch (piece) {
+		case 100: case 102: er = c.vocab_size; ec = c.dim; break;
+		case 101: case P_ATT_NORM: case P_FFN_NORM: er = c.dim; is_norm = true; break;
+		case P_Q: er = m->q_dim; ec = c.dim; break;
+		case P_K: case P_V: er = m->kv_dim; ec = c.dim; break;
+		case P_O: er = c.dim; ec = m->q_dim; break;
+		case P_GATE: case P_UP: er = c.hidden_dim; ec = c.dim; break;
+		case P_DOWN: er = c.dim; ec = c.hidden_dim; break;
+	}
+	if ((is_norm && (rank != 1 || shape[0] != er)) || (!is_norm && (rank != 2 || shape[0] != er || shape[1] != ec))) {
+		if (rank == 2) return set_error(XALM_ERR_INVALID, "shape mismatch for %s: [%d, %d] vs [%d, %d] expected!", name, shape[0], shape[1], er, ec);
+		return set_error(XALM_ERR_INVALID, "shape mismatch for %s: rank %d, [%d] vs [%d] expected!", name, rank, shape[0], er);
+	}
+	const size_t elems = is_norm ? (size_t) er : (size_t) er * ec;
+	if (elems % ti.block || (!is_norm && ec % ti.block)) return set_error(XALM_ERR_INVALID, "%s: row length %d is not a multiple of the block size %d", name, ec, ti.block);
+	if (nbytes != elems / ti.block * ti.bytes) return set_error(XALM_ERR_INVALID, "buffer size mismatch for %s: %zu vs %zu", name, nbytes, elems / ti.block * ti.bytes);
+	const uint8_t* host = (const uint8_t*) data;
+	cudaStream_t s = m->stream;
+	const int P = m->tp_size, R = m->tp_rank;
+
+	if (is_norm) {
+		if (type_id != XALM_F32 && type_id != XALM_BF16) return set_error(XALM_ERR_UNSUPPORTED, "rmsnorm: unsupported data type %d for %s", type_id, name);
+		uint8_t* d = nullptr;
+		XALM_TRY(m->da.alloc((void**) &d, nbytes));
+		XALM_CUDA_CHECK(cudaMemcpy(d, host, nbytes, cudaMemcpyHostToDevice));
+		if (piece == 101) { m->rms_final = d; m->rms_final_type = type_id; m->got_final_norm = true; }
+		else if (piece == P_ATT_NORM) { m->layers[layer].rms_att = d; m->layers[layer].rms_att_type = type_id; m->layers[layer].got[piece] = true; }
+		else { m->layers[layer].rms_ffn = d; m->layers[layer].rms_ffn_type = type_id; m->layers[layer].got[piece] = true; }
+		return XALM_OK;
+	}
+	if (type_id == XALM_U8) return set_error(XALM_ERR_UNSUPPORTED, "matmul: unsupported data type: U8 (%s)", name);
+
+	auto ensure = [&](WSlot& slot, int rows, int n) -> int {
+		if (slot.allocated) {
+			if (slot.m.type != type_id) return set_error(XALM_ERR_UNSUPPORTED, "%s: tensors fused into one matrix must share a type (%d vs %d)", name, type_id, slot.m.type);
+			return XALM_OK;
+		}
+		XALM_TRY(alloc_wmat(m->da, slot.m, type_id, rows, n));
+		slot.total_rows = rows;
+		slot.allocated = true;
+		return XALM_OK;
+	};
+
+	if (piece == 100 || piece == 102) {
+		if (piece == 100) {
+			// embedding table: replicated, kept in on-disk layout for the row gather
+			XALM_TRY(m->da.alloc((void**) &m->embed_raw, nbytes));
+			XALM_CUDA_CHECK(cudaMemcpy(m->embed_raw, host, nbytes, cudaMemcpyHostToDevice));
+			m->embed_type = type_id;
+			m->embed_row_bytes = (size_t) c.dim / ti.block * ti.bytes;
+			m->got_embed = true;
+			if (!c.tie_word_embeddings) return XALM_OK;
+			// tied: the classifier reads the same values (model.cpp:112-114) — built from this upload, no second host pass
+		} else if (c.tie_word_embeddings) {
+			return XALM_OK; // ignored, like the reference (model.cpp:112-114 loads embed.weight instead)
+		}
+		XALM_TRY(ensure(m->wcls, m->vocab_l, c.dim));
+		XALM_TRY(upload_piece(m->wcls.m, 0, type_id, host, c.dim, R * m->vocab_l, (R + 1) * m->vocab_l, 0, c.dim, m->staging, s));
+		m->got_cls = true;
+		return XALM_OK;
+	}
+
+	LayerDev& L = m->layers[layer];
+	L.piece_type[piece] = type_id;
+	switch (piece) {
+		case P_Q:
+			XALM_TRY(ensure(L.wqkv, m->q_dim_l + 2 * m->kv_dim_l, c.dim));
+			XALM_TRY(upload_piece(L.wqkv.m, 0, type_id, host, c.dim, R * m->q_dim_l, (R + 1) * m->q_dim_l, 0, c.dim, m->staging, s));
+			break;
+		case P_K:
+			XALM_TRY(ensure(L.wqkv, m->q_dim_l + 2 * m->kv_dim_l, c.dim));
+			XALM_TRY(upload_piece(L.wqkv.m, m->q_dim_l, type_id, host, c.dim, R * m->kv_dim_l, (R + 1) * m->kv_dim_l, 0, c.dim, m->staging, s));
+			break;
+		case P_V:
+			XALM_TRY(ensure(L.wqkv, m->q_dim_l + 2 * m->kv_dim_l, c.dim));
+			XALM_TRY(upload_piece(L.wqkv.m, m->q_dim_l + m->kv_dim_l, type_id, host, c.dim, R * m->kv_dim_l, (R + 1) * m->kv_dim_l, 0, c.dim, m->staging, s));
+			break;
+		case P_O: // row-split under TP = slice of the INPUT (quantised) axis
+			XALM_TRY(ensure(L.wo, c.dim, m->q_dim_l));
+			XALM_TRY(upload_piece(L.wo.m, 0, type_id, host, m->q_dim, 0, c.dim, R * m->q_dim_l, (R + 1) * m->q_dim_l, m->staging, s));
+			break;
+		case P_GATE:
+			XALM_TRY(ensure(L.w13, 2 * m->hidden_l, c.dim));
+			XALM_TRY(upload_piece(L.w13.m, 0, type_id, host, c.dim, R * m->hidden_l, (R + 1) * m->hidden_l, 0, c.dim, m->staging, s));
+			break;
+		case P_UP:
+			XALM_TRY(ensure(L.w13, 2 * m->hidden_l, c.dim));
+			XALM_TRY(upload_piece(L.w13.m, m->hidden_l, type_id, host, c.dim, R * m->hidden_l, (R + 1) * m->hidden_l, 0, c.dim, m->staging, s));
+			break;
+		case P_DOWN:
+			XALM_TRY(ensure(L.w2, c.dim, m->hidden_l));
+			XALM_TRY(upload_piece(L.w2.m, 0, type_id, host, c.hidden_dim, 0, c.dim, R * m->hidden_l, (R + 1) * m->hidden_l, m->staging, s));
+			break;
+	}
+	L.got[piece] = true;
+	(void) P;
+	return XALM_OK;
+}
+
+// ---- the per-token kernel sequence ---------------------------------------------------------------------------
+static int enqueue_token(xalm_cuda_model* m, int mode, cudaStream_t s, int* n_launches) {
+	const xalm_config& c = m->c;
+	const bool pdl = tune("pdl") != 0;
+	const bool tp = m->tp_size > 1;
+	int nl = 0;
+	cudaError_t e = launch(embed_kernel, dim3(4), dim3(256), s, false, m->embed_type, (const uint8_t*) m->embed_raw, m->embed_row_bytes,
+	                       c.dim, (const StepParams*) m->d_step, m->x);
+	if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "embed launch failed: %s", cudaGetErrorString(e));
+	nl++;
+	const int G = c.n_heads / c.n_kv_heads;
+	for (int l = 0; l < c.n_layers; l++) {
+		LayerDev& L = m->layers[l];
+		{ // attention pre-norm + q,k,v + clip + rope + KV write (+ sinks)
+			MatvecArgs a = {};
+			a.w = L.wqkv.m; a.x = m->x; a.n = c.dim; a.d = m->q_dim_l + 2 * m->kv_dim_l; a.epi = EPI_QKV;
+			a.norm_w = L.rms_att; a.norm_type = L.rms_att_type; a.norm_eps = c.norm_eps;
+			a.out = m->q; a.step = m->d_step; a.k_cache = L.k_cache; a.v_cache = L.v_cache; a.rope_freq = m->rope_freq;
+			a.q_dim = m->q_dim_l; a.kv_dim = m->kv_dim_l; a.head_dim = c.head_dim; a.qkv_clip = c.qkv_clip;
+			XALM_TRY(launch_matvec(a, s, pdl));
+			nl++;
+		}
+		{
+			AttnArgs a = {};
+			a.q = m->q; a.k_cache = L.k_cache; a.v_cache = L.v_cache; a.out = m->xb2; a.step = m->d_step; a.kv_len_fixed = -1;
+			a.n_kv_heads = m->n_kv_heads_l; a.n_splits = m->attn_splits; a.min_split = tune("attn_min_split");
+			a.part_acc = m->attn_acc; a.part_ml = m->attn_ml; a.tickets = m->tickets;
+			XALM_TRY(launch_attn(a, c.head_dim, G, s, pdl));
+			nl++;
+		}
+		{ // Wo + residual
+			MatvecArgs a = {};
+			a.w = L.wo.m; a.x = m->xb2; a.n = m->q_dim_l; a.d = c.dim;
+			a.epi = tp ? EPI_STORE : EPI_RESIDUAL; a.out = tp ? m->part : m->x;
+			XALM_TRY(launch_matvec(a, s, pdl));
+			nl++;
+			if (tp) {
+				XALM_NCCL_CHECK(g_nccl.AllReduce(m->part, m->part, c.dim, ncclFloat32, ncclSum, m->comm, s));
+				e = launch(residual_add_kernel, dim3(8), dim3(256), s, false, m->x, (const float*) m->part, c.dim);
+				if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "residual launch failed: %s", cudaGetErrorString(e));
+				nl += 2;
+			}
+		}
+		{ // ffn pre-norm + W1,W3 + act*gate
+			MatvecArgs a = {};
+			a.w = L.w13.m; a.x = m->x; a.n = c.dim; a.d = m->hidden_l; a.epi = EPI_GLU; a.glu_off = m->hidden_l; a.act = c.act;
+			a.norm_w = L.rms_ffn; a.norm_type = L.rms_ffn_type; a.norm_eps = c.norm_eps; a.out = m->hb;
+			XALM_TRY(launch_matvec(a, s, pdl && !tp));
+			nl++;
+		}
+		{ // W2 + residual
+			MatvecArgs a = {};
+			a.w = L.w2.m; a.x = m->hb; a.n = m->hidden_l; a.d = c.dim;
+			a.epi = tp ? EPI_STORE : EPI_RESIDUAL; a.out = tp ? m->part : m->x;
+			XALM_TRY(launch_matvec(a, s, pdl));
+			nl++;
+			if (tp) {
+				XALM_NCCL_CHECK(g_nccl.AllReduce(m->part, m->part, c.dim, ncclFloat32, ncclSum, m->comm, s));
+				e = launch(residual_add_kernel, dim3(8), dim3(256), s, false, m->x, (const float*) m->part, c.dim);
+				if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "residual launch failed: %s", cudaGetErrorString(e));
+				nl += 2;
+			}
+		}
+	}
+	if (mode == XALM_OUTPUT_LOGITS) { // final norm + classifier (infer.cpp:625-637)
+		MatvecArgs a = {};
+		a.w = m->wcls.m; a.x = m->x; a.n = c.dim; a.d = m->vocab_l; a.epi = EPI_STORE;
+		a.norm_w = m->rms_final; a.norm_type = m->rms_final_type; a.norm_eps = c.norm_eps; a.out = m->logits;
+		XALM_TRY(launch_matvec(a, s, pdl && !tp));
+		nl++;
+		if (tp) {
+			XALM_NCCL_CHECK(g_nccl.AllGather(m->logits, m->logits_full, m->vocab_l, ncclFloat32, m->comm, s));
+			nl++;
+		}
+	}
+	if (n_launches) *n_launches = nl;
+	return XALM_OK;
+}
+
+int xalm_cuda_finalize(xalm_cuda_model* m) {
+	if (!m) return set_error(XALM_ERR_INVALID, "model is NULL");
+	if (m->finalized) return XALM_OK;
+	XALM_CUDA_CHECK(cudaSetDevice(m->device));
+	const xalm_config& c = m->c;
+	if (!m->got_embed) return set_error(XALM_ERR_STATE, "missing tensor embed.weight");
+	if (!m->got_final_norm) return set_error(XALM_ERR_STATE, "missing tensor output.norm.weight");
+	if (!m->got_cls) return set_error(XALM_ERR_STATE, "missing tensor output.weight");
+	static const char* names[9] = {"attn.norm", "mlp.norm", "attn.q", "attn.k", "attn.v", "attn.down", "mlp.gate", "mlp.down", "mlp.up"};
+	for (int l = 0; l < c.n_layers; l++)
+		for (int p = 0; p < 9; p++)
+			if (!m->layers[l].got[p]) return set_error(XALM_ERR_STATE, "missing tensor l.%d.%s.weight", l, names[p]);
+	if (m->tp_size > 1 && !m->comm) return set_error(XALM_ERR_STATE, "tp_size %d but xalm_cuda_comm_init was not called", m->tp_size);
+	if (m->staging.p) { cudaFree(m->staging.p); m->staging.p = nullptr; m->staging.cap = 0; }
+
+	auto fzero = [&](float** p, size_t n) -> int {
+		XALM_TRY(m->da.alloc((void**) p, n * sizeof(float)));
+		XALM_CUDA_CHECK(cudaMemset(*p, 0, n * sizeof(float)));
+		return XALM_OK;
+	};
+	XALM_TRY(fzero(&m->x, c.dim));
+	XALM_TRY(fzero(&m->xb2, m->q_dim_l));
+	XALM_TRY(fzero(&m->hb, m->hidden_l));
+	XALM_TRY(fzero(&m->q, m->q_dim_l));
+	XALM_TRY(fzero(&m->logits, m->vocab_l));
+	XALM_TRY(fzero(&m->part, c.dim));
+	if (m->tp_size > 1) XALM_TRY(fzero(&m->logits_full, c.vocab_size));
+	else m->logits_full = m->logits;
+	const size_t kv_elems = (size_t) c.max_seq_len * m->kv_dim_l;
+	for (auto& L : m->layers) {
+		XALM_TRY(m->da.alloc((void**) &L.k_cache, kv_elems * sizeof(__half)));
+		XALM_TRY(m->da.alloc((void**) &L.v_cache, kv_elems * sizeof(__half)));
+		XALM_CUDA_CHECK(cudaMemset(L.k_cache, 0, kv_elems * sizeof(__half)));
+		XALM_CUDA_CHECK(cudaMemset(L.v_cache, 0, kv_elems * sizeof(__half)));
+	}
+	const std::vector<float> freq = rope_freq_table(c.head_dim, c.rotary_dim, c.rope_theta);
+	XALM_TRY(m->da.alloc((void**) &m->rope_freq, freq.size() * sizeof(float)));
+	XALM_CUDA_CHECK(cudaMemcpy(m->rope_freq, freq.data(), freq.size() * sizeof(float), cudaMemcpyHostToDevice));
+	const int G = c.n_heads / c.n_kv_heads;
+	m->attn_splits = attn_auto_splits(m->n_kv_heads_l);
+	XALM_TRY(fzero(&m->attn_acc, (size_t) m->n_kv_heads_l * m->attn_splits * G * c.head_dim));
+	XALM_TRY(fzero(&m->attn_ml, (size_t) m->n_kv_heads_l * m->attn_splits * G * 2));
+	XALM_TRY(m->da.alloc((void**) &m->tickets, m->n_kv_heads_l * sizeof(unsigned int)));
+	XALM_CUDA_CHECK(cudaMemset(m->tickets, 0, m->n_kv_heads_l * sizeof(unsigned int)));
+	XALM_TRY(m->da.alloc((void**) &m->d_step, sizeof(StepParams)));
+	XALM_CUDA_CHECK(cudaMallocHost((void**) &m->h_step, 64 * sizeof(StepParams)));
+	XALM_CUDA_CHECK(cudaMallocHost((void**) &m->h_logits, (size_t) c.vocab_size * sizeof(float)));
+	XALM_CUDA_CHECK(cudaDeviceSynchronize());
+	m->finalized = true;
+	return XALM_OK;
+}
+
+static int ensure_graph(xalm_cuda_model* m, int mode) {
+	if (m->graph[mode]) return XALM_OK;
+	cudaStream_t s = m->stream;
+	cudaGraph_t g = nullptr;
+	XALM_CUDA_CHECK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+	int nl = 0;
+	int rc = enqueue_token(m, mode, s, &nl);
+	cudaError_t e = cudaStreamEndCapture(s, &g);
+	if (rc != XALM_OK) { if (g) cudaGraphDestroy(g); return rc; }
+	if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+	e = cudaGraphInstantiate(&m->graph[mode], g, 0);
+	cudaGraphDestroy(g);
+	if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e));
+	m->launches_per_token[mode] = nl;
+	return XALM_OK;
+}
+
+int xalm_cuda_forward_async(xalm_cuda_model* m, int token, int pos, int mode) {
+	if (!m) return set_error(XALM_ERR_INVALID, "model is NULL");
+	if (!m->finalized) return set_error(XALM_ERR_STATE, "forward before finalize");
+	if (mode != XALM_HYDRATE_KV_CACHE && mode != XALM_OUTPUT_LOGITS) return set_error(XALM_ERR_INVALID, "bad mode %d", mode);
+	const xalm_config& c = m->c;
+	if (token < 0 || token >= c.vocab_size) return set_error(XALM_ERR_INVALID, "token %d out of range [0,%d)", token, c.vocab_size);
+	if (pos < 0) return set_error(XALM_ERR_INVALID, "negative position");
+	XALM_CUDA_CHECK(cudaSetDevice(m->device));
+	cudaStream_t s = m->stream;
+	// ring / sink index math: infer.cpp:611-613, KV_SINKS = 2 (model.h:10)
+	const int slot = m->step_slot;
+	m->step_slot = (slot + 1) % 64;
+	if (m->h_step_ev_used[slot]) XALM_CUDA_CHECK(cudaEventSynchronize(m->h_step_ev[slot]));
+	else { XALM_CUDA_CHECK(cudaEventCreateWithFlags(&m->h_step_ev[slot], cudaEventDisableTiming)); m->h_step_ev_used[slot] = true; }
+	StepParams& sp = m->h_step[slot];
+	sp.token = token; sp.pos = pos;
+	sp.kv_sink = pos >= c.max_seq_len ? 2 : 0;
+	sp.kv_pos = sp.kv_sink + (pos - sp.kv_sink) % (c.max_seq_len - sp.kv_sink);
+	sp.kv_len = pos >= c.max_seq_len ? c.max_seq_len : pos + 1;
+	sp.mode = mode;
+	XALM_CUDA_CHECK(cudaMemcpyAsync(m->d_step, &sp, sizeof sp, cudaMemcpyHostToDevice, s));
+	XALM_CUDA_CHECK(cudaEventRecord(m->h_step_ev[slot], s));
+	if (tune("graph")) {
+		XALM_TRY(ensure_graph(m, mode));
+		XALM_CUDA_CHECK(cudaGraphLaunch(m->graph[mode], s));
+		m->last_launches = m->launches_per_token[mode];
+	} else {
+		XALM_TRY(enqueue_token(m, mode, s, &m->last_launches));
+	}
+	return XALM_OK;
+}
+
+int xalm_cuda_sync(xalm_cuda_model* m) {
+	if (!m) return set_error(XALM_ERR_INVALID, "model is NULL");
+	XALM_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+	return XALM_OK;
+}
+
+int xalm_cuda_forward(xalm_cuda_model* m, int token, int pos, int mode, float* logits_host) {
+	XALM_TRY(xalm_cuda_forward_async(m, token, pos, mode));
+	if (mode == XALM_OUTPUT_LOGITS && logits_host) {
+		XALM_CUDA_CHECK(cudaMemcpyAsync(m->h_logits, m->logits_full, (size_t) m->c.vocab_size * sizeof(float), cudaMemcpyDeviceToHost, m->stream));
+		XALM_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+		if (logits_host != m->h_logits) memcpy(logits_host, m->h_logits, (size_t) m->c.vocab_size * sizeof(float));
+	} else {
+		XALM_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+	}
+	return XALM_OK;
+}
+
+float* xalm_cuda_logits_host(xalm_cuda_model* m) { return m ? m->h_logits : nullptr; }
+
+int xalm_cuda_last_launch_count(xalm_cuda_model* m, int* n) {
+	if (!m || !n) return set_error(XALM_ERR_INVALID, "NULL argument");
+	*n = m->last_launches;
+	return XALM_OK;
+}
+
+int xalm_cuda_active_bytes(xalm_cuda_model* m, long long pos, long long* bytes) {
+	if (!m || !bytes) return set_error(XALM_ERR_INVALID, "NULL argument");
+	if (!m->finalized) return set_error(XALM_ERR_STATE, "active_bytes before finalize");
+	const xalm_config& c = m->c;
+	auto wb = [](int type, long long elems) -> long long {
+		TypeInfo ti;
+		type_info(type, &ti);
+		return elems / ti.block * ti.bytes;
+	};
+	long long b = 0;
+	b += wb(m->embed_type, c.dim);
+	b += wb(m->rms_final_type, c.dim);
+	b += wb(m->wcls.m.type, (long long) m->vocab_l * c.dim);
+	for (auto& L : m->layers) {
+		b += wb(L.rms_att_type, c.dim) + wb(L.rms_ffn_type, c.dim);
+		b += wb(L.wqkv.m.type, (long long) (m->q_dim_l + 2 * m->kv_dim_l) * c.dim);
+		b += wb(L.wo.m.type, (long long) c.dim * m->q_dim_l);
+		b += wb(L.w13.m.type, 2LL * m->hidden_l * c.dim);
+		b += wb(L.w2.m.type, (long long) c.dim * m->hidden_l);
+		const long long kv_len = pos + 1 < c.max_seq_len ? pos + 1 : c.max_seq_len;
+		b += 2 * kv_len * m->kv_dim_l * 2;
+	}
+	*bytes = b;
+	return XALM_OK;
+}
+
+int xalm_cuda_read_state(xalm_cuda_model* m, int which, float* dst, size_t n) {
+	if (!m || !dst) return set_error(XALM_ERR_INVALID, "NULL argument");
+	if (!m->finalized) return set_error(XALM_ERR_STATE, "read_state before finalize");
+	const float* src = nullptr;
+	size_t cap = 0;
+	switch (which) {
+		case XALM_S_X: src = m->x; cap = m->c.dim; break;
+		case XALM_S_XB2: src = m->xb2; cap = m->q_dim_l; break;
+		case XALM_S_HB: src = m->hb; cap = m->hidden_l; break;
+		case XALM_S_Q: src = m->q; cap = m->q_dim_l; break;
+		case XALM_S_LOGITS: src = m->logits_full; cap = m->c.vocab_size; break;
+		default: return set_error(XALM_ERR_INVALID, "state buffer %d is not materialised by the fused kernels", which);
+	}
+	if (n > cap) return set_error(XALM_ERR_INVALID, "read_state: %zu > %zu", n, cap);
+	XALM_CUDA_CHECK(cudaSetDevice(m->device));
+	XALM_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+	XALM_CUDA_CHECK(cudaMemcpy(dst, src, n * sizeof(float), cudaMemcpyDeviceToHost));
+	return XALM_OK;
+}
+
+int xalm_cuda_read_kv(xalm_cuda_model* m, int layer, int which, uint16_t* dst, size_t n_elems) {
+	if (!m || !dst) return set_error(XALM_ERR_INVALID, "NULL argument");
+	if (!m->finalized) return set_error(XALM_ERR_STATE, "read_kv before finalize");
+	if (layer < 0 || layer >= m->c.n_layers || (which != 0 && which != 1)) return set_error(XALM_ERR_INVALID, "bad layer/which");
+	const size_t cap = (size_t) m->c.max_seq_len * m->kv_dim_l;
+	if (n_elems > cap) return set_error(XALM_ERR_INVALID, "read_kv: %zu > %zu", n_elems, cap);
+	XALM_CUDA_CHECK(cudaSetDevice(m->device));
+	XALM_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+	XALM_CUDA_CHECK(cudaMemcpy(dst, which == 0 ? m->layers[layer].k_cache : m->layers[layer].v_cache, n_elems * sizeof(uint16_t), cudaMemcpyDeviceToHost));
+	return XALM_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// op-level entry points (host in / host out) — the same kernels the model path launches
+// ---------------------------------------------------------------------------------------------------------
+struct TmpDev {
+	std::vector<void*> v;
+	~TmpDev() { for (void* p : v) cudaFree(p); }
+	int alloc(void** p, size_t n) {
+		cudaError_t e = cudaMalloc(p, n ? n : 16);
+		if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "cudaMalloc(%zu) failed: %s", n, cudaGetErrorString(e));
+		v.push_back(*p);
+		return XALM_OK;
+	}
+	int put(void** p, const void* h, size_t n) {
+		XALM_TRY(alloc(p, n));
+		XALM_CUDA_CHECK(cudaMemcpy(*p, h, n, cudaMemcpyHostToDevice));
+		return XALM_OK;
+	}
+};
+
+static int need_device() {
+	int n = 0;
+	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e != cudaSuccess || n == 0) return set_error(XALM_ERR_CUDA, "no CUDA device: %s", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+	return XALM_OK;
+}
+
+int xalm_cuda_dequant(int type_id, const void* src, size_t n_elems, float* dst) {
+	if (!src || !dst) return set_error(XALM_ERR_INVALID, "NULL argument");
+	TypeInfo ti;
+	if (!type_info(type_id, &ti)) return set_error(XALM_ERR_INVALID, "invalid type: %d", type_id);
+	if (n_elems % ti.block) return set_error(XALM_ERR_INVALID, "%zu elements is not a multiple of the block size %d", n_elems, ti.block);
+	XALM_TRY(need_device());
+	if (n_elems == 0) return XALM_OK;
+	TmpDev t;
+	void *d_src, *d_dst;
+	XALM_TRY(t.put(&d_src, src, n_elems / ti.block * ti.bytes));
+	XALM_TRY(t.alloc(&d_dst, n_elems * sizeof(float)));
+	dequant_kernel<<<1024, 256>>>(type_id, (const uint8_t*) d_src, n_elems, (float*) d_dst);
+	XALM_CUDA_CHECK(cudaGetLastError());
+	XALM_CUDA_CHECK(cudaMemcpy(dst, d_dst, n_elems * sizeof(float), cudaMemcpyDeviceToHost));
+	return XALM_OK;
+}
+
+// device-resident weight from host bytes via the same repack path the model upload uses
+static int tmp_weight(TmpDev& t, WMat& w, int type_id, const void* host, int rows, int n) {
+	TypeInfo ti;
+	if (!type_info(type_id, &ti)) return set_error(XALM_ERR_INVALID, "invalid type: %d", type_id);
+	if (type_id == XALM_U8) return set_error(XALM_ERR_UNSUPPORTED, "matmul: unsupported data type: U8");
+	if (n % ti.block) return set_error(XALM_ERR_INVALID, "row length %d is not a multiple of the block size %d", n, ti.block);
+	DevAlloc da;
+	int rc = alloc_wmat(da, w, type_id, rows, n);
+	for (void* p : da.ptrs) t.v.push_back(p);
+	XALM_TRY(rc);
+	Staging st;
+	rc = upload_piece(w, 0, type_id, (const uint8_t*) host, n, 0, rows, 0, n, st, 0);
+	if (st.p) t.v.push_back(st.p);
+	if (st.flag) t.v.push_back(st.flag);
+	return rc;
+}
+
+int xalm_cuda_matmul(float* xout, const float* x, const void* w, int type_id, int n, int d) {
+	if (!xout || !x || !w) return set_error(XALM_ERR_INVALID, "NULL argument");
+	if (n <= 0 || d <= 0 || n % 32 || d % 32) return set_error(XALM_ERR_INVALID, "matmul: n=%d d=%d must be positive multiples of 32", n, d);
+	XALM_TRY(need_device());
+	TmpDev t;
+	WMat wm;
+	XALM_TRY(tmp_weight(t, wm, type_id, w, d, n));
+	void *dx, *dy;
+	XALM_TRY(t.put(&dx, x, (size_t) n * sizeof(float)));
+	XALM_TRY(t.alloc(&dy, (size_t) d * sizeof(float)));
+	MatvecArgs a = {};
+	a.w = wm; a.x = (const float*) dx; a.n = n; a.d = d; a.epi = EPI_STORE; a.out = (float*) dy;
+	XALM_TRY(launch_matvec(a, 0, false));
+	XALM_CUDA_CHECK(cudaMemcpy(xout, dy, (size_t) d * sizeof(float), cudaMemcpyDeviceToHost));
+	return XALM_OK;
+}
+
+int xalm_cuda_mha(float* xout, float* att, const uint16_t* kb, const uint16_t* vb, const float* q, int head_dim, int kv_len,
+                  int max_seq_len, int n_heads, int n_kv_heads) {
+	if (!xout || !kb || !vb || !q) return set_error(XALM_ERR_INVALID, "NULL argument");
+	if (head_dim <= 0 || n_heads <= 0 || n_kv_heads <= 0 || n_heads % n_kv_heads || kv_len <= 0 || kv_len > max_seq_len)
+		return set_error(XALM_ERR_INVALID, "mha: bad dimensions");
+	XALM_TRY(need_device());
+	TmpDev t;
+	const size_t kv_bytes = (size_t) max_seq_len * n_kv_heads * head_dim * sizeof(uint16_t);
+	void *dk, *dv, *dq, *dout, *dacc, *dml, *dtick, *datt = nullptr;
+	XALM_TRY(t.put(&dk, kb, kv_bytes));
+	XALM_TRY(t.put(&dv, vb, kv_bytes));
+	XALM_TRY(t.put(&dq, q, (size_t) n_heads * head_dim * sizeof(float)));
+	XALM_TRY(t.alloc(&dout, (size_t) n_heads * head_dim * sizeof(float)));
+	const int G = n_heads / n_kv_heads;
+	const int splits = attn_auto_splits(n_kv_heads);
+	XALM_TRY(t.alloc(&dacc, (size_t) n_kv_heads * splits * G * head_dim * sizeof(float)));
+	XALM_TRY(t.alloc(&dml, (size_t) n_kv_heads * splits * G * 2 * sizeof(float)));
+	XALM_TRY(t.alloc(&dtick, n_kv_heads * sizeof(unsigned int)));
+	XALM_CUDA_CHECK(cudaMemset(dtick, 0, n_kv_heads * sizeof(unsigned int)));
+	AttnArgs a = {};
+	a.q = (const float*) dq; a.k_cache = (const __half*) dk; a.v_cache = (const __half*) dv; a.out = (float*) dout;
+	a.kv_len_fixed = kv_len; a.n_kv_heads = n_kv_heads; a.n_splits = splits; a.min_split = tune("attn_min_split");
+	a.part_acc = (float*) dacc; a.part_ml = (float*) dml; a.tickets = (unsigned int*) dtick;
+	XALM_TRY(launch_attn(a, head_dim, G, 0, false));
+	if (att) {
+		XALM_TRY(t.alloc(&datt, (size_t) n_heads * max_seq_len * sizeof(float)));
+		XALM_CUDA_CHECK(cudaMemset(datt, 0, (size_t) n_heads * max_seq_len * sizeof(float)));
+		attn_probs_kernel<<<n_heads, 256>>>((const float*) dq, (const __half*) dk, (float*) datt, head_dim, n_kv_heads, n_heads, kv_len, max_seq_len);
+		XALM_CUDA_CHECK(cudaGetLastError());
+		XALM_CUDA_CHECK(cudaMemcpy(att, datt, (size_t) n_heads * max_seq_len * sizeof(float), cudaMemcpyDeviceToHost));
+	}
+	XALM_CUDA_CHECK(cudaMemcpy(xout, dout, (size_t) n_heads * head_dim * sizeof(float), cudaMemcpyDeviceToHost));
+	return XALM_OK;
+}
+
+int xalm_cuda_rmsnorm(float* o, const float* x, const void* weight, int weight_type, int size, float eps) {
+	if (!o || !x || !weight || size <= 0) return set_error(XALM_ERR_INVALID, "bad argument");
+	if (weight_type != XALM_F32 && weight_type != XALM_BF16) return set_error(XALM_ERR_UNSUPPORTED, "rmsnorm: unsupported data type %d", weight_type);
+	XALM_TRY(need_device());
+	TmpDev t;
+	void *dx, *dw, *dout;
+	XALM_TRY(t.put(&dx, x, (size_t) size * sizeof(float)));
+	XALM_TRY(t.put(&dw, weight, (size_t) size * (weight_type == XALM_F32 ? 4 : 2)));
+	XALM_TRY(t.alloc(&dout, (size_t) size * sizeof(float)));
+	rmsnorm_kernel<<<1, 256>>>((float*) dout, (const float*) dx, (const uint8_t*) dw, weight_type, size, eps);
+	XALM_CUDA_CHECK(cudaGetLastError());
+	XALM_CUDA_CHECK(cudaMemcpy(o, dout, (size_t) size * sizeof(float), cudaMemcpyDeviceToHost));
+	return XALM_OK;
+}
+
+int xalm_cuda_rope(float* vec, int d, int head_dim, int pos, float theta, int rotary_dim) {
+	if (!vec || d <= 0 || d % 2 || head_dim <= 0 || head_dim % 2 || d % head_dim || rotary_dim < 0)
+		return set_error(XALM_ERR_INVALID, "rope: bad argument");
+	XALM_TRY(need_device());
+	TmpDev t;
+	const std::vector<float> freq = rope_freq_table(head_dim, rotary_dim, theta);
+	void *dv, *df;
+	XALM_TRY(t.put(&dv, vec, (size_t) d * sizeof(float)));
+	XALM_TRY(t.put(&df, freq.data(), freq.size() * sizeof(float)));
+	rope_kernel<<<(d / 2 + 255) / 256, 256>>>((float*) dv, d, head_dim, pos, (const float*) df);
+	XALM_CUDA_CHECK(cudaGetLastError());
+	XALM_CUDA_CHECK(cudaMemcpy(vec, dv, (size_t) d * sizeof(float), cudaMemcpyDeviceToHost));
+	return XALM_OK;
+}
+
+int xalm_cuda_ffn(float* xout, const float* x, const void* w1, const void* w2, const void* w3, int type_id, int hidden_dim, int dim,
+                  int act) {
+	if (!xout || !x || !w1 || !w2 || !w3) return set_error(XALM_ERR_INVALID, "NULL argument");
+	if (dim <= 0 || hidden_dim <= 0 || dim % 32 || hidden_dim % 32) return set_error(XALM_ERR_INVALID, "ffn: dims must be positive multiples of 32");
+	if (act != XALM_GELU && act != XALM_SILU) return set_error(XALM_ERR_UNSUPPORTED, "unsupported activation type");
+	XALM_TRY(need_device());
+	TypeInfo ti;
+	if (!type_info(type_id, &ti)) return set_error(XALM_ERR_INVALID, "invalid type: %d", type_id);
+	TmpDev t;
+	// W1|W3 stacked along rows, exactly as the model path fuses gate|up
+	DevAlloc da;
+	WMat w13;
+	int rc = alloc_wmat(da, w13, type_id, 2 * hidden_dim, dim);
+	for (void* p : da.ptrs) t.v.push_back(p);
+	XALM_TRY(rc);
+	Staging st;
+	rc = upload_piece(w13, 0, type_id, (const uint8_t*) w1, dim, 0, hidden_dim, 0, dim, st, 0);
+	if (rc == XALM_OK) rc = upload_piece(w13, hidden_dim, type_id, (const uint8_t*) w3, dim, 0, hidden_dim, 0, dim, st, 0);
+	if (st.p) t.v.push_back(st.p);
+	if (st.flag) t.v.push_back(st.flag);
+	XALM_TRY(rc);
+	WMat wd;
+	XALM_TRY(tmp_weight(t, wd, type_id, w2, dim, hidden_dim));
+	void *dx, *dhb, *dout;
+	XALM_TRY(t.put(&dx, x, (size_t) dim * sizeof(float)));
+	XALM_TRY(t.alloc(&dhb, (size_t) hidden_dim * sizeof(float)));
+	XALM_TRY(t.alloc(&dout, (size_t) dim * sizeof(float)));
+	MatvecArgs a = {};
+	a.w = w13; a.x = (const float*) dx; a.n = dim; a.d = hidden_dim; a.epi = EPI_GLU; a.glu_off = hidden_dim; a.act = act; a.out = (float*) dhb;
+	XALM_TRY(launch_matvec(a, 0, false));
+	MatvecArgs b = {};
+	b.w = wd; b.x = (const float*) dhb; b.n = hidden_dim; b.d = dim; b.epi = EPI_STORE; b.out = (float*) dout;
+	XALM_TRY(launch_matvec(b, 0, false));
+	XALM_CUDA_CHECK(cudaMemcpy(xout, dout, (size_t) dim * sizeof(float), cudaMemcpyDeviceToHost));
+	return XALM_OK;
+}
+
+int xalm_cuda_bench_matvec(int type_id, int n, int d, int n_buffers, int iters, float* ms_per_launch) {
+	if (!ms_per_launch || n <= 0 || d <= 0 || n % 32 || d % 32 || n_buffers <= 0 || iters <= 0) return set_error(XALM_ERR_INVALID, "bad argument");
+	XALM_TRY(need_device());
+	TypeInfo ti;
+	if (!type_info(type_id, &ti)) return set_error(XALM_ERR_INVALID, "invalid type: %d", type_id);
+	if (n % ti.block) return set_error(XALM_ERR_INVALID, "n %% block");
+	DevAlloc da;
+	std::vector<WMat> ws(n_buffers);
+	const size_t raw_bytes = (size_t) d * n / ti.block * ti.bytes;
+	// random but decodable bytes: scales must be finite f16 -> build on host once
+	std::vector<uint8_t> host(raw_bytes);
+	uint32_t st = 12345;
+	for (size_t i = 0; i < raw_bytes; i++) { st = st * 1664525u + 1013904223u; host[i] = (uint8_t) ((st >> 24) & 0x3F); }
+	int rc = XALM_OK;
+	Staging sg;
+	for (int b = 0; b < n_buffers && rc == XALM_OK; b++) {
+		rc = alloc_wmat(da, ws[b], type_id, d, n);
+		if (rc == XALM_OK) rc = upload_piece(ws[b], 0, type_id, host.data(), n, 0, d, 0, n, sg, 0);
+	}
+	float *dx = nullptr, *dy = nullptr;
+	if (rc == XALM_OK) rc = da.alloc((void**) &dx, (size_t) n * sizeof(float));
+	if (rc == XALM_OK) rc = da.alloc((void**) &dy, (size_t) d * sizeof(float));
+	if (rc == XALM_OK) {
+		std::vector<float> hx(n, 0.01f);
+		cudaMemcpy(dx, hx.data(), (size_t) n * sizeof(float), cudaMemcpyHostToDevice);
+		cudaEvent_t e0, e1;
+		cudaEventCreate(&e0); cudaEventCreate(&e1);
+		cudaStream_t s;
+		cudaStreamCreate(&s);
+		const bool pdl = tune("pdl") != 0;
+		for (int it = -3 * n_buffers; it < iters && rc == XALM_OK; it++) {
+			if (it == 0) cudaEventRecord(e0, s);
+			MatvecArgs a = {};
+			a.w = ws[((it % n_buffers) + n_buffers) % n_buffers]; a.x = dx; a.n = n; a.d = d; a.epi = EPI_STORE; a.out = dy;
+			rc = launch_matvec(a, s, pdl);
+		}
+		cudaEventRecord(e1, s);
+		cudaError_t e = cudaStreamSynchronize(s);
+		if (rc == XALM_OK && e != cudaSuccess) rc = set_error(XALM_ERR_CUDA, "bench failed: %s", cudaGetErrorString(e));
+		float ms = 0.f;
+		cudaEventElapsedTime(&ms, e0, e1);
+		*ms_per_launch = ms / iters;
+		cudaEventDestroy(e0); cudaEventDestroy(e1); cudaStreamDestroy(s);
+	}
+	if (sg.p) cudaFree(sg.p);
+	if (sg.flag) cudaFree(sg.flag);
+	da.free_all();
+	return rc;
+}
+
+} // extern "C"
