@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py — Mistral-7B batch-1 decode throughput on N B200s (BASELINE.json metric), with roofline and CPU baseline.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--shape m7] [--wtype q8_0] [--ctx 4096]
+
+A "step" is one decoded token: one pass of the hot path (embed -> 32 x [norm+QKV+rope+KV, attention, Wo+residual,
+norm+W1|W3+GLU, W2+residual] -> norm+classifier).  The workload is BASELINE config[1]: Mistral-7B-v0.2 architecture,
+random-init weights N(0, 0.02^2) quantised to q8_0 with the reference's own quantiser rules, batch 1, 4k context; the K
+timed tokens sit at positions spread uniformly over [0, ctx) (the fp16 KV ring is fully allocated, so attention streams
+kv_len rows of it exactly as a hydrated cache would).  Weights (7.5 GB) are far larger than L2 (126 MB), so every step
+streams them from HBM; no L2 flush is needed between steps.
+
+`value`  : tokens/s, device-timed (CUDA events on the launch stream, max over ranks), weights + KV resident in HBM.
+`e2e`    : the same loop through the public API (Model.forward + Sampler.sample_argmax on HOST logits): every step
+           copies the step's inputs (token, position: one 32-byte StepParams from pinned memory) host->device and the
+           logits (vocab * 4 bytes) device->host, and is timed by the wall clock around the synchronous calls.
+`--impl reference` : the reference's CPU path (oracle/ restatement; the reference C++ does not build on x86)
+           on all host cores, same model, one token per step.
+N > 1    : tensor parallel over N GPUs (one process per GPU, strong scaling: same model, sharded).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+SMI_QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 200 ms while the timed region runs."""
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={SMI_QUERY}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.25)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self) -> dict:
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs() -> tuple:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def positions_for(steps: int, ctx: int) -> list:
+    if steps <= 1:
+        return [ctx - 1]
+    return [int(round(i * (ctx - 1) / (steps - 1))) for i in range(steps)]
+
+
+def build_model_streaming(cfg_full: dict, cfg: dict, wtype, seed: int, keep_host: bool, **cuda_kw):
+    """Generate the synthetic checkpoint tensor by tensor and upload each as it is made (peak host RAM = one tensor
+    unless keep_host, which the CPU baseline needs)."""
+    import ctypes as C
+    from xalm_b200 import capi, synth
+    from xalm_b200.model import Model
+    model = Model(cfg, {})
+    L = capi.lib()
+    h = C.c_void_p()
+    xc = capi.XalmConfig.from_dict(cfg)
+    capi.check(L.xalm_cuda_create(C.byref(xc), cuda_kw.get("device", 0), cuda_kw.get("tp_rank", 0), cuda_kw.get("tp_size", 1), C.byref(h)))
+    model._h = h
+    model.tp_rank, model.tp_size = cuda_kw.get("tp_rank", 0), cuda_kw.get("tp_size", 1)
+    if cuda_kw.get("stream") is not None:
+        capi.check(L.xalm_cuda_set_stream(h, C.c_void_p(cuda_kw["stream"])))
+    if model.tp_size > 1:
+        buf = (C.c_char * 128).from_buffer_copy(cuda_kw["comm_id"])
+        capi.check(L.xalm_cuda_comm_init(h, buf))
+    from xalm_b200 import xalm_file as X
+    shapes = X.expected_tensors(cfg)
+    host = {}
+    for name, t, arr in synth.iter_tensors(cfg_full, wtype, seed):
+        raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
+        model.upload(name, t, shapes[name], raw)
+        if keep_host:
+            host[name] = (t.id, raw)
+    capi.check(L.xalm_cuda_finalize(h))
+    return model, host
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path (oracle port; DESIGN.md explains why the C++ cannot be built
+    here) on all host cores.  Under torchrun only rank 0 works."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    from oracle import oracle
+    from xalm_b200 import synth, types as T, xalm_file as X
+    cfg_full = synth.model_config(args.shape)
+    cfg = X.parse_config(synth.metadata_strings(cfg_full), args.ctx)
+    wtype = T.parse(args.wtype)
+    cores = os.cpu_count() or 1
+    t0 = time.time()
+    tensors = {name: (t.id, np.ascontiguousarray(arr).view(np.uint8).reshape(-1)) for name, t, arr in synth.iter_tensors(cfg_full, wtype, args.seed)}
+    gen_s = time.time() - t0
+    om = oracle.OracleModel(cfg, tensors, acc_mode=1)
+    tok = 1
+    for i in range(args.warmup):
+        lg = om.forward(tok, i, 1)
+        tok = oracle.sample_argmax(lg)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        lg = om.forward(tok, args.warmup + i, 1)
+        tok = oracle.sample_argmax(lg)
+    dt = time.perf_counter() - t0
+    tps = args.steps / dt
+    sample = f"{args.steps} greedy tokens at positions {args.warmup}..{args.warmup + args.steps - 1} of the same {args.shape} {args.wtype} model (full depth), wall clock"
+    line = {
+        "impl": "reference", "metric": "decode_tokens_per_s", "value": tps, "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, cfg),
+        "cpu_baseline": {"value": tps, "unit": "tok/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": tps, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "notes": f"oracle/liboracle.so (restatement of src/infer.cpp), OpenMP over {cores} host cores; weights generated in {gen_s:.0f}s",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, cfg) -> dict:
+    return {"workload": f"{args.shape} ({'Mistral-7B-v0.2' if args.shape == 'm7' else args.shape} architecture) random-init {args.wtype}, "
+                        f"batch-1 decode, 4k context" if args.ctx == 4096 else f"{args.shape} {args.wtype} batch-1 decode ctx {args.ctx}",
+            "shape": args.shape, "weight_format": args.wtype, "context": cfg["max_seq_len"], "batch": 1,
+            "positions": "spread uniformly over [0, context)", "l2": "inputs larger than L2 (weights streamed from HBM every step)",
+            "parallelism": f"tp{args.gpus}"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=256)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shape", default="m7")
+    ap.add_argument("--wtype", default="q8_0")
+    ap.add_argument("--ctx", type=int, default=4096)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-tokens", type=int, default=6, help="tokens the CPU baseline decodes (rank 0, N=1)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from xalm_b200 import capi, synth, types as T, xalm_file as X
+    from xalm_b200.model import InferenceState, Sampler
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run --nproc-per-node {args.gpus}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the backend has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
+        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 8) // world))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    cfg_full = synth.model_config(args.shape)
+    cfg = X.parse_config(synth.metadata_strings(cfg_full), args.ctx)
+    wtype = T.parse(args.wtype)
+    comm_id = None
+    if world > 1:
+        from xalm_b200.model import Model
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt = torch.frombuffer(bytearray(Model.comm_unique_id()), dtype=torch.uint8).cuda()
+        dist.broadcast(idt, 0)
+        comm_id = bytes(idt.cpu().numpy().tobytes())
+    stream = torch.cuda.current_stream().cuda_stream
+    keep_host = (world == 1 and rank == 0 and not args.no_cpu_baseline)
+    t0 = time.time()
+    model, host_tensors = build_model_streaming(cfg_full, cfg, wtype, args.seed, keep_host, device=local_rank, tp_rank=rank,
+                                                tp_size=world, comm_id=comm_id, stream=stream)
+    gen_s = time.time() - t0
+    ctx = cfg["max_seq_len"]
+    pos_list = positions_for(args.steps, ctx)
+    rng = np.random.default_rng(123)
+    toks = [int(t) for t in rng.integers(3, cfg["vocab_size"], size=args.steps + args.warmup)]
+
+    # ---- device-timed: weights and KV resident, logits stay on the device ----
+    for i in range(args.warmup):
+        model.forward_async(toks[i], pos_list[min(i, len(pos_list) - 1)], 1)
+    model.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        e0.record()
+        for i in range(args.steps):
+            model.forward_async(toks[args.warmup + i], pos_list[i], 1)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = model.last_launch_count() * args.steps
+        # ---- end to end through the public API: host token in, host logits out, host sampler ----
+        state = InferenceState(cfg).cuda()
+        sampler = Sampler(cfg)
+        tok = toks[0]
+        for i in range(3):
+            model.forward(state, tok, pos_list[i % len(pos_list)], 1)
+            tok = sampler.sample_argmax(state)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            model.forward(state, tok, pos_list[i], 1)
+            tok = sampler.sample_argmax(state)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1])
+    tps = args.steps / (ms / 1e3)
+    e2e_tps = args.steps / e2e_s
+
+    # ---- roofline: whole step, and the dominant kernel (fused norm + gate|up matvec) timed alone ----
+    peak, peak_src = measured_peak_gbs()
+    step_bytes = float(np.mean([model.active_bytes(p) for p in pos_list]))          # this rank's shard
+    step_gbs = step_bytes * args.steps / (ms / 1e3) / 1e9
+    hidden_l = cfg["hidden_dim"] // world
+    k_bytes = 2 * hidden_l * cfg["dim"] * wtype.bytes // wtype.block
+    nbuf = max(2, int(np.ceil(600e6 / k_bytes)))
+    k_ms = capi.bench_matvec(wtype.id, cfg["dim"], hidden_l, nbuf, 200, epi=2, with_norm=True)
+    k_gbs = k_bytes / (k_ms / 1e3) / 1e9
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "kernel_traffic.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get(f"{args.shape}_{args.wtype}_w13_bytes")
+        except Exception:
+            traffic = None
+
+    line = {
+        "metric": "decode_tokens_per_s", "value": tps, "unit": "tok/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(args, cfg),
+        "e2e": {"value": e2e_tps, "unit": "tok/s", "h2d_bytes_per_step": 32, "d2h_bytes_per_step": cfg["vocab_size"] * 4},
+        "gpu_launches": launches,
+        "clocks": clocks.summary(),
+        "roofline": {"bound": "hbm", "achieved": k_gbs, "peak": peak, "unit": "GB/s", "frac": k_gbs / peak, "traffic": traffic,
+                     "kernel": f"matvec_kernel<{args.wtype}, norm+gate|up+GLU> {2 * hidden_l}x{cfg['dim']}", "bytes_per_launch": k_bytes,
+                     "ms_per_launch": k_ms, "peak_source": peak_src, "timing": "CUDA events around 200 back-to-back launches on rotating buffers > L2"},
+        "step_roofline": {"bytes_per_step": step_bytes, "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
+                          "frac_of_8000": step_gbs / 8000.0, "formula": "Model::active_bytes(pos) (model.cpp:12-35), mean over the timed positions"},
+        "notes": f"weights generated+uploaded in {gen_s:.0f}s; host cores {os.cpu_count()}",
+    }
+
+    # ---- CPU baseline beside it: the oracle port on the host cores, same weights (rank 0, N = 1 only) ----
+    if keep_host:
+        from oracle import oracle
+        om = oracle.OracleModel(cfg, host_tensors, acc_mode=1)
+        tok = 1
+        lg = om.forward(tok, 0, 1)          # warm-up (touches every page)
+        t0 = time.perf_counter()
+        n = args.cpu_tokens
+        for i in range(n):
+            tok = oracle.sample_argmax(lg)
+            lg = om.forward(tok, 1 + i, 1)
+        cdt = time.perf_counter() - t0
+        om.close()
+        line["cpu_baseline"] = {"value": n / cdt, "unit": "tok/s", "cores": os.cpu_count(), "kind": "port",
+                                "sample": f"{n} greedy tokens at positions 1..{n} of the same model (full depth, same weights), wall clock"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    model.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

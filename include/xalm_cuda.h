@@ -141,9 +141,11 @@ int xalm_cuda_ffn(float* xout, const float* x, const void* w1, const void* w2, c
 int xalm_cuda_tune(const char* key, int value);
 
 /* ---- kernel micro-benchmark hook (bench.py roofline leg; README.md:62-84 `-k matmul`) ------------------- */
-/* Times `iters` launches of the matvec kernel on a resident (d,n) weight of `type_id` (random bytes), rotating over
- * `n_buffers` distinct copies so the working set exceeds L2.  Returns mean milliseconds per launch. */
-int xalm_cuda_bench_matvec(int type_id, int n, int d, int n_buffers, int iters, float* ms_per_launch);
+/* Times `iters` back-to-back launches of the matvec kernel on resident weights of `type_id` (random bytes), rotating
+ * over `n_buffers` distinct copies so the working set exceeds L2.  epi: 0 = plain store of d outputs from a (d,n) matrix,
+ * 2 = the fused gate|up kernel (2d rows -> d outputs through act*gate); with_norm: fuse the rmsnorm prologue.  Returns
+ * mean milliseconds per launch (CUDA events on the launch stream). */
+int xalm_cuda_bench_matvec(int type_id, int n, int d, int epi, int with_norm, int n_buffers, int iters, float* ms_per_launch);
 
 #ifdef __cplusplus
 }

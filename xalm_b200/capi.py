@@ -66,7 +66,7 @@ SYMBOLS = {
     "xalm_cuda_rope": (_i, [_vp, _i, _i, _i, C.c_float, _i]),
     "xalm_cuda_ffn": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
     "xalm_cuda_tune": (_i, [C.c_char_p, _i]),
-    "xalm_cuda_bench_matvec": (_i, [_i, _i, _i, _i, _i, _fp]),
+    "xalm_cuda_bench_matvec": (_i, [_i, _i, _i, _i, _i, _i, _i, _fp]),
 }
 
 _LIB = None
@@ -159,7 +159,7 @@ def ffn(x, w1, w2, w3, type_id, hidden_dim, dim, act):
     return out
 
 
-def bench_matvec(type_id: int, n: int, d: int, n_buffers: int, iters: int) -> float:
+def bench_matvec(type_id: int, n: int, d: int, n_buffers: int, iters: int, epi: int = 0, with_norm: bool = False) -> float:
     ms = C.c_float(0)
-    check(lib().xalm_cuda_bench_matvec(type_id, n, d, n_buffers, iters, C.byref(ms)))
+    check(lib().xalm_cuda_bench_matvec(type_id, n, d, epi, int(with_norm), n_buffers, iters, C.byref(ms)))
     return ms.value

@@ -1109,15 +1109,17 @@ int xalm_cuda_ffn(float* xout, const float* x, const void* w1, const void* w2, c
 	return XALM_OK;
 }
 
-int xalm_cuda_bench_matvec(int type_id, int n, int d, int n_buffers, int iters, float* ms_per_launch) {
+int xalm_cuda_bench_matvec(int type_id, int n, int d, int epi, int with_norm, int n_buffers, int iters, float* ms_per_launch) {
 	if (!ms_per_launch || n <= 0 || d <= 0 || n % 32 || d % 32 || n_buffers <= 0 || iters <= 0) return set_error(XALM_ERR_INVALID, "bad argument");
 	XALM_TRY(need_device());
 	TypeInfo ti;
 	if (!type_info(type_id, &ti)) return set_error(XALM_ERR_INVALID, "invalid type: %d", type_id);
 	if (n % ti.block) return set_error(XALM_ERR_INVALID, "n %% block");
+	if (epi != EPI_STORE && epi != EPI_GLU) return set_error(XALM_ERR_INVALID, "bench epi must be 0 (store) or 2 (glu)");
+	const int rows = epi == EPI_GLU ? 2 * d : d;
 	DevAlloc da;
 	std::vector<WMat> ws(n_buffers);
-	const size_t raw_bytes = (size_t) d * n / ti.block * ti.bytes;
+	const size_t raw_bytes = (size_t) rows * n / ti.block * ti.bytes;
 	// random but decodable bytes: scales must be finite f16 -> build on host once
 	std::vector<uint8_t> host(raw_bytes);
 	uint32_t st = 12345;
@@ -1125,10 +1127,17 @@ int xalm_cuda_bench_matvec(int type_id, int n, int d, int n_buffers, int iters, 
 	int rc = XALM_OK;
 	Staging sg;
 	for (int b = 0; b < n_buffers && rc == XALM_OK; b++) {
-		rc = alloc_wmat(da, ws[b], type_id, d, n);
-		if (rc == XALM_OK) rc = upload_piece(ws[b], 0, type_id, host.data(), n, 0, d, 0, n, sg, 0);
+		rc = alloc_wmat(da, ws[b], type_id, rows, n);
+		if (rc == XALM_OK) rc = upload_piece(ws[b], 0, type_id, host.data(), n, 0, rows, 0, n, sg, 0);
 	}
-	float *dx = nullptr, *dy = nullptr;
+	float *dx = nullptr, *dy = nullptr, *dg = nullptr;
+	if (rc == XALM_OK && with_norm) {
+		rc = da.alloc((void**) &dg, (size_t) n * sizeof(float));
+		if (rc == XALM_OK) {
+			std::vector<float> hg(n, 1.0f);
+			cudaMemcpy(dg, hg.data(), (size_t) n * sizeof(float), cudaMemcpyHostToDevice);
+		}
+	}
 	if (rc == XALM_OK) rc = da.alloc((void**) &dx, (size_t) n * sizeof(float));
 	if (rc == XALM_OK) rc = da.alloc((void**) &dy, (size_t) d * sizeof(float));
 	if (rc == XALM_OK) {
@@ -1142,7 +1151,9 @@ int xalm_cuda_bench_matvec(int type_id, int n, int d, int n_buffers, int iters, 
 		for (int it = -3 * n_buffers; it < iters && rc == XALM_OK; it++) {
 			if (it == 0) cudaEventRecord(e0, s);
 			MatvecArgs a = {};
-			a.w = ws[((it % n_buffers) + n_buffers) % n_buffers]; a.x = dx; a.n = n; a.d = d; a.epi = EPI_STORE; a.out = dy;
+			a.w = ws[((it % n_buffers) + n_buffers) % n_buffers]; a.x = dx; a.n = n; a.d = d; a.epi = epi; a.out = dy;
+			a.glu_off = d; a.act = XALM_SILU;
+			if (with_norm) { a.norm_w = (const uint8_t*) dg; a.norm_type = XALM_F32; a.norm_eps = 1e-5f; }
 			rc = launch_matvec(a, s, pdl);
 		}
 		cudaEventRecord(e1, s);
