@@ -231,7 +231,10 @@ def main():
             idt = torch.frombuffer(bytearray(Model.comm_unique_id()), dtype=torch.uint8).cuda()
         dist.broadcast(idt, 0)
         comm_id = bytes(idt.cpu().numpy().tobytes())
-    stream = torch.cuda.current_stream().cuda_stream
+    # a dedicated (non-default) torch stream: the backend launches on it and torch.cuda.Event times it
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
     keep_host = (world == 1 and rank == 0 and not args.no_cpu_baseline)
     t0 = time.time()
     model, host_tensors = build_model_streaming(cfg_full, cfg, wtype, args.seed, keep_host, device=local_rank, tp_rank=rank,

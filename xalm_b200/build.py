@@ -53,18 +53,19 @@ def build_cuda(force: bool = False, verbose: bool = False, extra=()) -> str:
 
 
 def build_host(force: bool = False) -> str:
+    """libxalm_host.so: format writers + synthetic generator (no CUDA dependency, loaded by synth.py).
+    xalm_main: the C++ host executable (reference CLI surface) linked against libxalm_cuda.so."""
     hdir = os.path.join(CSRC, "host")
-    srcs = [s for s in _sources(hdir, (".cpp",))]
-    if not srcs:
-        return ""
-    deps = srcs + _sources(hdir, (".h",)) + [os.path.join(ROOT, "include", "xalm_cuda.h")]
-    lib_srcs = [s for s in srcs if not s.endswith("main.cpp")]
+    deps = _sources(hdir, (".cpp", ".h")) + [os.path.join(ROOT, "include", "xalm_cuda.h")]
     common = [GXX, "-O2", "-std=c++20", "-fPIC", "-fopenmp", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", hdir]
-    if force or not _newer(HOSTLIB, deps):
-        subprocess.check_call([*common, "-shared", "-o", HOSTLIB, *lib_srcs, "-ldl"])
+    quant = os.path.join(hdir, "quantize.cpp")
+    if force or not _newer(HOSTLIB, [quant]):
+        subprocess.check_call([*common, "-shared", "-o", HOSTLIB, quant])
     main_src = os.path.join(hdir, "main.cpp")
-    if os.path.exists(main_src) and (force or not _newer(MAIN, deps)):
-        subprocess.check_call([*common, "-o", MAIN, main_src, *lib_srcs, "-ldl", f"-Wl,-rpath,{HERE}"])
+    if os.path.exists(main_src) and (force or not _newer(MAIN, deps + [LIB])):
+        build_cuda()
+        subprocess.check_call([*common, "-o", MAIN, main_src, os.path.join(hdir, "model.cpp"), quant, "-L", HERE, "-lxalm_cuda",
+                               "-Wl,-rpath,$ORIGIN"])
     return HOSTLIB
 
 

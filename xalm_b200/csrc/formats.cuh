@@ -138,6 +138,7 @@ struct WMat {
 	int rows = 0;
 	int n = 0;
 	int flags = 0; // bit0: fp8 tensor contains codes an IEEE decoder maps to NaN/Inf -> take the exact LUT path
+	int layout_units = 0; // block format stored unit-interleaved for the TMA kernel (matvec_tma.cuh) instead of planar
 	const uint8_t* p0 = nullptr;
 	const uint8_t* p1 = nullptr;
 	const uint8_t* p2 = nullptr;

@@ -25,6 +25,7 @@
 
 #include "attention.cuh"
 #include "matvec.cuh"
+#include "matvec_tma.cuh"
 
 namespace xalm {
 
@@ -50,6 +51,10 @@ static std::map<std::string, int>& tuning() {
 	    {"attn_splits", 0},  // 0 = auto (~2 CTAs per SM)
 	    {"attn_min_split", 128},
 	    {"mv_cfg_rows", 0},  // 0 = auto, 1 = force config A (R4 KS1 NW4), 2 = force config B (R2 KS4 NW8)
+	    {"tma", 1},          // stream weights with cp.async.bulk into a shared-memory ring (matvec_tma.cuh)
+	    {"tma_smem_kb", 100}, // shared-memory budget per CTA for the TMA kernel (two kernels co-reside under PDL)
+	    {"tma_rc_small", 4}, // rows per tile when the matrix has few rows (Wo, W2)
+	    {"tma_ctas_per_sm", 1},
 	};
 	return t;
 }
@@ -64,6 +69,21 @@ static int tune(const char* k) {
 // ---------------------------------------------------------------------------------------------------------
 // launch helper (optionally with the programmatic-stream-serialisation attribute = PDL)
 // ---------------------------------------------------------------------------------------------------------
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_smem(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, Args&&... args) {
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = grid;
+	cfg.blockDim = block;
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream = stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+	attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+	cfg.attrs = attr;
+	cfg.numAttrs = 1;
+	return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 template <typename... KArgs, typename... Args>
 static cudaError_t launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, bool pdl, Args&&... args) {
 	cudaLaunchConfig_t cfg = {};
@@ -103,6 +123,123 @@ static cudaError_t launch_matvec_typed(const MatvecArgs& a, const MvCfg& c, bool
 	return launch(matvec_kernel<TYPE, 2, 4, 8, false>, grid, block, s, pdl, a);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// TMA matvec dispatch (matvec_tma.cuh)
+// ---------------------------------------------------------------------------------------------------------
+static int g_num_sms = 0;
+static int num_sms() {
+	if (!g_num_sms) {
+		int dev = 0;
+		g_num_sms = 148;
+		if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+	}
+	return g_num_sms;
+}
+
+template <int TYPE, int RC, int KW, bool NORM>
+static cudaError_t launch_tma_inst(const TmaArgs& ta, int grid, size_t smem, cudaStream_t s, bool pdl) {
+	static bool attr_set = false;
+	auto kern = matvec_tma_kernel<TYPE, RC, KW, NORM>;
+	if (!attr_set) {
+		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+		if (e != cudaSuccess) return e;
+		attr_set = true;
+	}
+	return launch_smem(kern, dim3(grid), dim3((TMA_NW + 1) * 32), smem, s, pdl, ta);
+}
+
+template <int TYPE>
+static cudaError_t launch_tma_typed(const TmaArgs& ta, int RC, int KW, bool norm, int grid, size_t smem, cudaStream_t s, bool pdl) {
+#define XALM_TMA_CASE(rc, kw)                                                                     \
+	if (RC == rc && KW == kw)                                                                     \
+		return norm ? launch_tma_inst<TYPE, rc, kw, true>(ta, grid, smem, s, pdl)                 \
+		            : launch_tma_inst<TYPE, rc, kw, false>(ta, grid, smem, s, pdl);
+	XALM_TMA_CASE(8, 8)
+	XALM_TMA_CASE(8, 4)
+	XALM_TMA_CASE(4, 8)
+#undef XALM_TMA_CASE
+	return cudaErrorInvalidValue;
+}
+
+static int pieces_per_unit(int t) {
+	switch (t) {
+		case XALM_F32: return 64;
+		case XALM_F16: case XALM_BF16: return 32;
+		case XALM_Q4_0: case XALM_Q4_1: case XALM_Q5_0: case XALM_Q5_1: return 8;
+		default: return 16;
+	}
+}
+
+// can this matrix go down the TMA path?
+static bool tma_eligible(const WMat& w, int n) {
+	if (!tune("tma")) return false;
+	if (!unit_bytes(w.type) || n % 256) return false;
+	if ((w.type == XALM_F8_E4M3 || w.type == XALM_F8_E5M2) && (w.flags & WMAT_FP8_NONFINITE)) return false;
+	return true;
+}
+
+static int launch_matvec_tma(const MatvecArgs& a, cudaStream_t s, bool pdl) {
+	const int t = a.w.type;
+	const int vrows = a.epi == EPI_GLU ? 2 * a.d : a.d;
+	const int ppu = pieces_per_unit(t);
+	const int nu = a.n / 256;
+	const int sms = num_sms() * tune("tma_ctas_per_sm");
+	// rows per tile: 8, or fewer when the matrix is too short to give every SM a few tiles
+	int RC = 8, KW = 8;
+	if (vrows / 8 < 6 * sms && tune("tma_rc_small") == 4 && ppu >= 16) RC = 4;
+	if (ppu == 8) { RC = 8; KW = 4; }                       // 4/5-bit: 8 pieces per unit -> fewer K-slices
+	if (RC == 8 && KW == 8 && nu * ppu / 8 < 32) KW = 4;     // short rows: keep 32 lanes busy
+	const int force = tune("mv_cfg_rows");
+	if (force == 88) { RC = 8; KW = 8; }
+	if (force == 84) { RC = 8; KW = 4; }
+	if (force == 48) { RC = 4; KW = 8; }
+	if (vrows % RC) return -1;
+	const int ub = unit_bytes(t);
+	const size_t budget = (size_t) tune("tma_smem_kb") * 1024;
+	const size_t fixed = tma_smem_bytes(t, a.n, RC, 0, 0) + 2 * 4 * sizeof(uint64_t);
+	if (fixed + 2 * (size_t) RC * ub > 200 * 1024) return -1; // activations do not fit: LDG path
+	// stage: U units per row, chosen to keep >= 32 pieces per K-slice, as large as the budget allows with >= 2 stages
+	int umin = (32 * KW + ppu - 1) / ppu;
+	if (umin > nu) umin = nu;
+	int U = umin, NS = 2;
+	size_t best = 0;
+	for (int u = umin; u <= nu && u <= 64; u++) {
+		if (u != nu && (u % umin)) continue;
+		const size_t stage = (size_t) RC * u * ub;
+		size_t avail = budget > fixed ? budget - fixed : 0;
+		int ns = (int) (avail / stage);
+		if (ns > 4) ns = 4;
+		if (ns < 2) continue;
+		if ((size_t) ns * stage > best) { best = (size_t) ns * stage; U = u; NS = ns; }
+	}
+	if (best == 0) { U = umin; NS = 2; }
+	const size_t smem = tma_smem_bytes(t, a.n, RC, U, NS);
+	if (smem > 200 * 1024) return -1;
+	TmaArgs ta;
+	ta.a = a;
+	ta.U = U; ta.NS = NS;
+	ta.n_tiles = (vrows + RC - 1) / RC;
+	const int grid = ta.n_tiles < sms ? ta.n_tiles : sms;
+	const bool norm = a.norm_w != nullptr;
+	cudaError_t e;
+	switch (t) {
+		case XALM_F32: e = launch_tma_typed<XALM_F32>(ta, RC, KW, norm, grid, smem, s, pdl); break;
+		case XALM_F16: e = launch_tma_typed<XALM_F16>(ta, RC, KW, norm, grid, smem, s, pdl); break;
+		case XALM_BF16: e = launch_tma_typed<XALM_BF16>(ta, RC, KW, norm, grid, smem, s, pdl); break;
+		case XALM_F8_E4M3: e = launch_tma_typed<XALM_F8_E4M3>(ta, RC, KW, norm, grid, smem, s, pdl); break;
+		case XALM_F8_E5M2: e = launch_tma_typed<XALM_F8_E5M2>(ta, RC, KW, norm, grid, smem, s, pdl); break;
+		case XALM_Q8: e = launch_tma_typed<XALM_Q8>(ta, RC, KW, norm, grid, smem, s, pdl); break;
+		case XALM_Q8_0: e = launch_tma_typed<XALM_Q8_0>(ta, RC, KW, norm, grid, smem, s, pdl); break;
+		case XALM_Q4_0: e = launch_tma_typed<XALM_Q4_0>(ta, RC, KW, norm, grid, smem, s, pdl); break;
+		case XALM_Q4_1: e = launch_tma_typed<XALM_Q4_1>(ta, RC, KW, norm, grid, smem, s, pdl); break;
+		case XALM_Q5_0: e = launch_tma_typed<XALM_Q5_0>(ta, RC, KW, norm, grid, smem, s, pdl); break;
+		case XALM_Q5_1: e = launch_tma_typed<XALM_Q5_1>(ta, RC, KW, norm, grid, smem, s, pdl); break;
+		default: return -1;
+	}
+	if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "matvec (tma) launch failed: %s", cudaGetErrorString(e));
+	return XALM_OK;
+}
+
 static int launch_matvec(MatvecArgs a, cudaStream_t s, bool pdl) {
 	const bool norm = a.norm_w != nullptr;
 	if (norm && a.norm_type != XALM_F32 && a.norm_type != XALM_BF16)
@@ -112,6 +249,15 @@ static int launch_matvec(MatvecArgs a, cudaStream_t s, bool pdl) {
 	const int vrows = a.epi == EPI_GLU ? 2 * a.d : a.d;
 	int t = a.w.type;
 	cudaError_t e;
+	if (a.w.layout_units) {
+		const int rc = launch_matvec_tma(a, s, pdl);
+		if (rc >= 0) return rc;
+		return set_error(XALM_ERR_STATE, "matrix is in unit layout but the TMA kernel cannot take it (n=%d d=%d)", a.n, a.d);
+	}
+	if (tma_eligible(a.w, a.n)) {
+		const int rc = launch_matvec_tma(a, s, pdl);
+		if (rc >= 0) return rc;
+	}
 	if (t == XALM_TQ1_0) {
 		if (a.n % 256) return set_error(XALM_ERR_INVALID, "TQ1_0 rows must be a multiple of 256 elements (n=%d)", a.n);
 		dim3 grid((vrows + 4 * 4 - 1) / (4 * 4)), block(4 * 32);
@@ -273,8 +419,19 @@ struct WSlot {
 };
 
 static int alloc_wmat(DevAlloc& da, WMat& m, int type, int rows, int n) {
+	m.type = type; m.rows = rows; m.n = n; m.flags = 0; m.layout_units = 0;
+	TypeInfo tinfo;
+	type_info(type, &tinfo);
+	if (tinfo.block > 1 && unit_bytes(type) && n % 256 == 0 && rows % 8 == 0 && tune("tma")) {
+		// block formats on the TMA path: unit-interleaved rows (matvec_tma.cuh); same byte count as planar
+		m.layout_units = 1;
+		m.s0 = (size_t) n / 256 * unit_bytes(type); m.s1 = m.s2 = 0;
+		uint8_t* p = nullptr;
+		XALM_TRY(da.alloc((void**) &p, m.s0 * rows));
+		m.p0 = p; m.p1 = m.p2 = nullptr;
+		return XALM_OK;
+	}
 	const PlaneSizes ps = plane_row_bytes(type, n);
-	m.type = type; m.rows = rows; m.n = n; m.flags = 0;
 	m.s0 = ps.s0; m.s1 = ps.s1; m.s2 = ps.s2;
 	uint8_t *p0 = nullptr, *p1 = nullptr, *p2 = nullptr;
 	XALM_TRY(da.alloc((void**) &p0, ps.s0 * rows));
@@ -314,7 +471,8 @@ static int upload_piece(WMat& m, int dst_row, int type, const uint8_t* host, int
 	uint8_t* p0 = const_cast<uint8_t*>(m.p0) + (size_t) dst_row * m.s0;
 	uint8_t* p1 = m.p1 ? const_cast<uint8_t*>(m.p1) + (size_t) dst_row * m.s1 : nullptr;
 	uint8_t* p2 = m.p2 ? const_cast<uint8_t*>(m.p2) + (size_t) dst_row * m.s2 : nullptr;
-	repack_kernel<<<1024, 256, 0, s>>>(type, st.p, width, rows, n, p0, m.s0, p1, m.s1, p2, m.s2);
+	if (m.layout_units) repack_units_kernel<<<1024, 256, 0, s>>>(type, st.p, width, rows, n, p0, m.s0);
+	else repack_kernel<<<1024, 256, 0, s>>>(type, st.p, width, rows, n, p0, m.s0, p1, m.s1, p2, m.s2);
 	XALM_CUDA_CHECK(cudaGetLastError());
 	if (type == XALM_F8_E4M3 || type == XALM_F8_E5M2) {
 		XALM_CUDA_CHECK(cudaMemsetAsync(st.flag, 0, sizeof(int), s));
