@@ -140,6 +140,11 @@ int xalm_cuda_ffn(float* xout, const float* x, const void* w1, const void* w2, c
  * environment variable overrides the stored value.  Takes effect for graphs captured afterwards. */
 int xalm_cuda_tune(const char* key, int value);
 
+/* In-kernel timeline (there is no nsys here): with out == NULL start recording up to n_records kernels; with out != NULL
+ * stop and fetch the records — 4 x u64 each: kernel id (100+epi = TMA matvec, 200+epi = LDG matvec, 300 = attention),
+ * %globaltimer (ns) of block 0 at entry, after the dependency wait, at exit. */
+int xalm_cuda_timeline(int n_records, unsigned long long* out, int* n_out);
+
 /* ---- kernel micro-benchmark hook (bench.py roofline leg; README.md:62-84 `-k matmul`) ------------------- */
 /* Times `iters` back-to-back launches of the matvec kernel on resident weights of `type_id` (random bytes), rotating
  * over `n_buffers` distinct copies so the working set exceeds L2.  epi: 0 = plain store of d outputs from a (d,n) matrix,

@@ -66,6 +66,7 @@ SYMBOLS = {
     "xalm_cuda_rope": (_i, [_vp, _i, _i, _i, C.c_float, _i]),
     "xalm_cuda_ffn": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i]),
     "xalm_cuda_tune": (_i, [C.c_char_p, _i]),
+    "xalm_cuda_timeline": (_i, [_i, _vp, C.POINTER(_i)]),
     "xalm_cuda_bench_matvec": (_i, [_i, _i, _i, _i, _i, _i, _i, _fp]),
 }
 
@@ -157,6 +158,17 @@ def ffn(x, w1, w2, w3, type_id, hidden_dim, dim, act):
     check(lib().xalm_cuda_ffn(_p(out), _p(x), _p(np.ascontiguousarray(w1)), _p(np.ascontiguousarray(w2)),
                               _p(np.ascontiguousarray(w3)), type_id, hidden_dim, dim, act))
     return out
+
+
+def timeline_start(n_records: int):
+    check(lib().xalm_cuda_timeline(n_records, None, None))
+
+
+def timeline_stop(n_records: int) -> np.ndarray:
+    out = np.zeros((n_records, 4), dtype=np.uint64)
+    n = C.c_int(0)
+    check(lib().xalm_cuda_timeline(n_records, _p(out), C.byref(n)))
+    return out[: n.value]
 
 
 def bench_matvec(type_id: int, n: int, d: int, n_buffers: int, iters: int, epi: int = 0, with_norm: bool = False) -> float:

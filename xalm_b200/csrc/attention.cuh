@@ -53,7 +53,10 @@ __global__ void __launch_bounds__(NW * 32) attn_decode_kernel(const AttnArgs a) 
 	__shared__ bool s_last;
 
 	pdl_launch_dependents();
+	int tl = -1;
+	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) tl = tl_begin(300);
 	pdl_wait();
+	tl_mark(tl, 2);
 
 	const int kvh = blockIdx.y, split = blockIdx.x;
 	const int kv_len = a.kv_len_fixed >= 0 ? a.kv_len_fixed : a.step->kv_len;
@@ -205,6 +208,7 @@ __global__ void __launch_bounds__(NW * 32) attn_decode_kernel(const AttnArgs a) 
 		if (s_last) a.tickets[kvh] = 0; // ready for the next launch
 	}
 	__syncthreads();
+	tl_mark(tl, 3);
 	if (!s_last) return;
 	__threadfence();
 	const float* bacc = a.part_acc + (size_t) kvh * a.n_splits * G * HD;

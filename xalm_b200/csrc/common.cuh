@@ -91,6 +91,31 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
 	return r;
 }
 
+// ---- optional in-kernel timeline (debug/profiling: no nsys in this environment).  When enabled, block 0 of every kernel
+//      records %globaltimer at entry, after the dependency wait and at exit. ----
+struct Timeline {
+	unsigned long long* buf; // 4 x u64 per record: kernel id, t_entry, t_after_wait, t_exit
+	unsigned int cap;
+	unsigned int count;
+};
+__device__ Timeline d_timeline = {nullptr, 0, 0}; // single translation unit
+__device__ __forceinline__ unsigned long long gtime() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+	return t;
+}
+__device__ __forceinline__ int tl_begin(int kid) {
+	if (d_timeline.buf == nullptr) return -1;
+	const unsigned int slot = atomicAdd(&d_timeline.count, 1u);
+	if (slot >= d_timeline.cap) return -1;
+	d_timeline.buf[4 * slot] = (unsigned long long) kid;
+	d_timeline.buf[4 * slot + 1] = gtime();
+	return (int) slot;
+}
+__device__ __forceinline__ void tl_mark(int slot, int which) {
+	if (slot >= 0) d_timeline.buf[4 * slot + which] = gtime();
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

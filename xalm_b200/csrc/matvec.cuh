@@ -154,6 +154,8 @@ __global__ void __launch_bounds__(NW * 32) matvec_kernel(const MatvecArgs a) {
 	const bool active = row0 < vrows;
 
 	pdl_launch_dependents();
+	int tl = -1;
+	if (blockIdx.x == 0 && threadIdx.x == 0) tl = tl_begin(200 + a.epi);
 
 	RowPtr rp[R];
 #pragma unroll
@@ -176,6 +178,7 @@ __global__ void __launch_bounds__(NW * 32) matvec_kernel(const MatvecArgs a) {
 	}
 
 	pdl_wait(); // activations (and the KV ring) written by earlier kernels are visible from here on
+	tl_mark(tl, 2);
 
 	if (a.epi == EPI_QKV && blockIdx.x == 0 && a.step->kv_sink > 0) rotate_sinks(a, a.step->kv_sink);
 
@@ -277,6 +280,7 @@ __global__ void __launch_bounds__(NW * 32) matvec_kernel(const MatvecArgs a) {
 			epilogue<R>(a, row0, y);
 		}
 	}
+	tl_mark(tl, 3);
 }
 
 // ---- TQ1_0 (quants.py:664-683): 256 weights in 54 bytes, base-3 packed.  Not a 16-byte-chunk format: one warp

@@ -229,18 +229,19 @@ __global__ void __launch_bounds__((TMA_NW + 1) * 32, 1) matvec_tma_kernel(const 
 	}
 	__syncthreads();
 	pdl_launch_dependents();
+	int tl = -1;
+	if (blockIdx.x == 0 && threadIdx.x == 0) tl = tl_begin(100 + a.epi);
 
 	const int my_tiles = ((int) blockIdx.x < ta.n_tiles) ? (ta.n_tiles - 1 - (int) blockIdx.x) / (int) gridDim.x + 1 : 0;
 
 	if (warp == TMA_NW) {
 		// ===================== producer: weights only — runs ahead of griddepcontrol.wait =====================
 		if (lane == 0) {
-			int it = 0;
+			int slot = 0, phase = 0;
 			for (int tt = 0; tt < my_tiles; tt++) {
 				const int row0 = ((int) blockIdx.x + tt * (int) gridDim.x) * RC;
-				for (int st = 0; st < stages_per_tile; st++, it++) {
-					const int slot = it % NS;
-					mbar_wait(&empty[slot], ((it / NS) & 1) ^ 1);
+				for (int st = 0; st < stages_per_tile; st++) {
+					mbar_wait(&empty[slot], phase ^ 1);
 					const int u0 = st * U;
 					const int un = min(U, nu - u0);
 					const uint32_t bytes = (uint32_t) un * UB;
@@ -251,6 +252,7 @@ __global__ void __launch_bounds__((TMA_NW + 1) * 32, 1) matvec_tma_kernel(const 
 						const int pr = phys_row(a, row0, r, RC);
 						bulk_g2s(dst + (size_t) r * row_stage_bytes, a.w.p0 + (size_t) pr * a.w.s0 + (size_t) u0 * UB, bytes, &full[slot]);
 					}
+					if (++slot == NS) { slot = 0; phase ^= 1; }
 				}
 			}
 		}
@@ -259,6 +261,7 @@ __global__ void __launch_bounds__((TMA_NW + 1) * 32, 1) matvec_tma_kernel(const 
 
 	// ===================== consumers =====================
 	pdl_wait(); // activations / KV ring of earlier kernels are visible from here on
+	tl_mark(tl, 2);
 	if (a.epi == EPI_QKV && blockIdx.x == 0 && a.step->kv_sink > 0) {
 		const int pairs = a.kv_dim / 2;
 		for (int i = threadIdx.x; i < a.step->kv_sink * pairs; i += TMA_NW * 32) {
@@ -271,10 +274,17 @@ __global__ void __launch_bounds__((TMA_NW + 1) * 32, 1) matvec_tma_kernel(const 
 	}
 	// ---- stage activations: xb = NORM ? x * scale * g : x ----
 	{
+		// xb is stored permuted inside each 256-element unit: the E floats a lane needs for one piece are split into
+		// E/4 float4s laid out [i][piece], so the 32 lanes of a warp read consecutive float4s (no bank conflicts).
+		auto xpos = [](int e) { // e % 4 == 0
+			const int u = e >> 8, w = e & 255;
+			const int pp = w / E, i4 = (w % E) >> 2;
+			return (u << 8) + ((i4 * PPU + pp) << 2);
+		};
 		float ss = 0.f;
 		for (int i = threadIdx.x * 4; i < a.n; i += TMA_NW * 32 * 4) {
 			const float4 v = ld_act4(a.x + i);
-			*reinterpret_cast<float4*>(xb + i) = v;
+			*reinterpret_cast<float4*>(xb + xpos(i)) = v;
 			ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
 		}
 		if (NORM) {
@@ -286,7 +296,7 @@ __global__ void __launch_bounds__((TMA_NW + 1) * 32, 1) matvec_tma_kernel(const 
 			for (int i = 0; i < TMA_NW; i++) tot += s_red[i];
 			const float scale = 1.0f / sqrtf(tot / (float) a.n + a.norm_eps);
 			for (int i = threadIdx.x * 4; i < a.n; i += TMA_NW * 32 * 4) { // same elements this thread wrote above
-				float4 v = *reinterpret_cast<float4*>(xb + i);
+				float4 v = *reinterpret_cast<float4*>(xb + xpos(i));
 				float4 g;
 				if (a.norm_type == XALM_F32) g = ld_act4(reinterpret_cast<const float*>(a.norm_w) + i);
 				else {
@@ -295,34 +305,33 @@ __global__ void __launch_bounds__((TMA_NW + 1) * 32, 1) matvec_tma_kernel(const 
 					                __uint_as_float(gv.y & 0xFFFF0000u));
 				}
 				v.x = v.x * scale * g.x; v.y = v.y * scale * g.y; v.z = v.z * scale * g.z; v.w = v.w * scale * g.w; // infer.cpp:233-235
-				*reinterpret_cast<float4*>(xb + i) = v;
+				*reinterpret_cast<float4*>(xb + xpos(i)) = v;
 			}
 		}
 		consumer_bar_sync();
 	}
 
 	const int kw = warp % KW, rw = warp / KW;
-	int it = 0;
+	int slot = 0, phase = 0;
 	for (int tt = 0; tt < my_tiles; tt++) {
 		f32x2 acc[R];
 #pragma unroll
 		for (int r = 0; r < R; r++) acc[r] = pack2(0.f, 0.f);
-		for (int st = 0; st < stages_per_tile; st++, it++) {
-			const int slot = it % NS;
+		for (int st = 0; st < stages_per_tile; st++) {
 			const int u0 = st * U;
 			const int un = min(U, nu - u0);
 			const int pieces = un * PPU;                 // pieces per row in this stage
 			const int per = (pieces + KW - 1) / KW;      // this warp's K-slice [kw*per, ...)
 			const int pend = min(pieces, (kw + 1) * per);
-			mbar_wait(&full[slot], (it / NS) & 1);
+			mbar_wait(&full[slot], phase);
 			const uint8_t* rows = ring + (size_t) slot * RC * row_stage_bytes + (size_t) (rw * R) * row_stage_bytes;
 			for (int p = kw * per + lane; p < pend; p += 32) {
 				const int u = p / PPU, pp = p % PPU;
 				float xv[E];
-				const float* xs = xb + (size_t) (u0 + u) * 256 + pp * E;
+				const float* xs = xb + (size_t) (u0 + u) * 256 + pp * 4;
 #pragma unroll
 				for (int i = 0; i < E; i += 4) {
-					const float4 v = *reinterpret_cast<const float4*>(xs + i);
+					const float4 v = *reinterpret_cast<const float4*>(xs + i * PPU);
 					xv[i] = v.x; xv[i + 1] = v.y; xv[i + 2] = v.z; xv[i + 3] = v.w;
 				}
 #pragma unroll
@@ -333,6 +342,7 @@ __global__ void __launch_bounds__((TMA_NW + 1) * 32, 1) matvec_tma_kernel(const 
 			}
 			__syncwarp();
 			if (lane == 0) mbar_arrive(&empty[slot]);
+			if (++slot == NS) { slot = 0; phase ^= 1; }
 		}
 		// ---- combine the KW K-slices (fixed order) and run the epilogue; barrier deferred behind the next tile's work ----
 		float* pt = part + (tt & 1) * (TMA_NW * 16);
@@ -373,6 +383,7 @@ __global__ void __launch_bounds__((TMA_NW + 1) * 32, 1) matvec_tma_kernel(const 
 			}
 		}
 	}
+	tl_mark(tl, 3);
 }
 
 } // namespace xalm

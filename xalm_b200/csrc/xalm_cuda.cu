@@ -53,8 +53,10 @@ static std::map<std::string, int>& tuning() {
 	    {"mv_cfg_rows", 0},  // 0 = auto, 1 = force config A (R4 KS1 NW4), 2 = force config B (R2 KS4 NW8)
 	    {"tma", 1},          // stream weights with cp.async.bulk into a shared-memory ring (matvec_tma.cuh)
 	    {"tma_smem_kb", 100}, // shared-memory budget per CTA for the TMA kernel (two kernels co-reside under PDL)
-	    {"tma_rc_small", 4}, // rows per tile when the matrix has few rows (Wo, W2)
-	    {"tma_ctas_per_sm", 1},
+	    {"tma_rc_small", 8}, // rows per tile when the matrix has few rows (Wo, W2)
+	    {"tma_rc", 0},       // 0 = auto, else force rows per tile (4 or 8)
+	    {"tma_ns_max", 4},   // most ring stages
+	    {"tma_ctas_per_sm", 2},
 	};
 	return t;
 }
@@ -137,14 +139,26 @@ static int num_sms() {
 }
 
 template <int TYPE, int RC, int KW, bool NORM>
-static cudaError_t launch_tma_inst(const TmaArgs& ta, int grid, size_t smem, cudaStream_t s, bool pdl) {
+static cudaError_t launch_tma_inst(const TmaArgs& ta, int max_ctas_per_sm, size_t smem, cudaStream_t s, bool pdl) {
 	static bool attr_set = false;
+	static std::map<size_t, int> occ_cache;
 	auto kern = matvec_tma_kernel<TYPE, RC, KW, NORM>;
 	if (!attr_set) {
 		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
 		if (e != cudaSuccess) return e;
 		attr_set = true;
 	}
+	// persistent grid: exactly as many CTAs as can be resident at once (a second wave would serialise behind the first)
+	auto it = occ_cache.find(smem);
+	if (it == occ_cache.end()) {
+		int occ = 1;
+		cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (TMA_NW + 1) * 32, smem);
+		if (e != cudaSuccess) return e;
+		it = occ_cache.emplace(smem, occ < 1 ? 1 : occ).first;
+	}
+	int per_sm = it->second < max_ctas_per_sm ? it->second : max_ctas_per_sm;
+	int grid = num_sms() * per_sm;
+	if (grid > ta.n_tiles) grid = ta.n_tiles;
 	return launch_smem(kern, dim3(grid), dim3((TMA_NW + 1) * 32), smem, s, pdl, ta);
 }
 
@@ -183,12 +197,14 @@ static int launch_matvec_tma(const MatvecArgs& a, cudaStream_t s, bool pdl) {
 	const int vrows = a.epi == EPI_GLU ? 2 * a.d : a.d;
 	const int ppu = pieces_per_unit(t);
 	const int nu = a.n / 256;
-	const int sms = num_sms() * tune("tma_ctas_per_sm");
+	const int sms = num_sms();
 	// rows per tile: 8, or fewer when the matrix is too short to give every SM a few tiles
 	int RC = 8, KW = 8;
 	if (vrows / 8 < 6 * sms && tune("tma_rc_small") == 4 && ppu >= 16) RC = 4;
 	if (ppu == 8) { RC = 8; KW = 4; }                       // 4/5-bit: 8 pieces per unit -> fewer K-slices
 	if (RC == 8 && KW == 8 && nu * ppu / 8 < 32) KW = 4;     // short rows: keep 32 lanes busy
+	if (tune("tma_rc") == 4 && ppu >= 16) { RC = 4; KW = 8; }
+	if (tune("tma_rc") == 8 && ppu >= 16) { RC = 8; KW = 8; }
 	const int force = tune("mv_cfg_rows");
 	if (force == 88) { RC = 8; KW = 8; }
 	if (force == 84) { RC = 8; KW = 4; }
@@ -208,7 +224,7 @@ static int launch_matvec_tma(const MatvecArgs& a, cudaStream_t s, bool pdl) {
 		const size_t stage = (size_t) RC * u * ub;
 		size_t avail = budget > fixed ? budget - fixed : 0;
 		int ns = (int) (avail / stage);
-		if (ns > 4) ns = 4;
+		if (ns > tune("tma_ns_max")) ns = tune("tma_ns_max");
 		if (ns < 2) continue;
 		if ((size_t) ns * stage > best) { best = (size_t) ns * stage; U = u; NS = ns; }
 	}
@@ -219,7 +235,7 @@ static int launch_matvec_tma(const MatvecArgs& a, cudaStream_t s, bool pdl) {
 	ta.a = a;
 	ta.U = U; ta.NS = NS;
 	ta.n_tiles = (vrows + RC - 1) / RC;
-	const int grid = ta.n_tiles < sms ? ta.n_tiles : sms;
+	const int grid = tune("tma_ctas_per_sm"); // upper bound on resident CTAs per SM; the launcher asks the occupancy API
 	const bool norm = a.norm_w != nullptr;
 	cudaError_t e;
 	switch (t) {
@@ -1264,6 +1280,37 @@ int xalm_cuda_ffn(float* xout, const float* x, const void* w1, const void* w2, c
 	b.w = wd; b.x = (const float*) dhb; b.n = hidden_dim; b.d = dim; b.epi = EPI_STORE; b.out = (float*) dout;
 	XALM_TRY(launch_matvec(b, 0, false));
 	XALM_CUDA_CHECK(cudaMemcpy(xout, dout, (size_t) dim * sizeof(float), cudaMemcpyDeviceToHost));
+	return XALM_OK;
+}
+
+int xalm_cuda_timeline(int n_records, unsigned long long* out, int* n_out) {
+	// n_records > 0 and out == NULL: start recording (up to n_records kernels); out != NULL: stop, copy records (4 x u64 each)
+	XALM_TRY(need_device());
+	static unsigned long long* dbuf = nullptr;
+	static int cap = 0;
+	XALM_CUDA_CHECK(cudaDeviceSynchronize());
+	if (!out) {
+		if (dbuf) cudaFree(dbuf);
+		dbuf = nullptr;
+		cap = n_records;
+		Timeline t = {nullptr, 0, 0};
+		if (n_records > 0) {
+			XALM_CUDA_CHECK(cudaMalloc((void**) &dbuf, (size_t) n_records * 4 * sizeof(unsigned long long)));
+			XALM_CUDA_CHECK(cudaMemset(dbuf, 0, (size_t) n_records * 4 * sizeof(unsigned long long)));
+			t.buf = dbuf; t.cap = (unsigned) n_records;
+		}
+		XALM_CUDA_CHECK(cudaMemcpyToSymbol(d_timeline, &t, sizeof t));
+		return XALM_OK;
+	}
+	Timeline t;
+	XALM_CUDA_CHECK(cudaMemcpyFromSymbol(&t, d_timeline, sizeof t));
+	int n = (int) (t.count < (unsigned) cap ? t.count : (unsigned) cap);
+	if (n > n_records) n = n_records;
+	if (n > 0) XALM_CUDA_CHECK(cudaMemcpy(out, dbuf, (size_t) n * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+	if (n_out) *n_out = n;
+	Timeline z = {nullptr, 0, 0};
+	XALM_CUDA_CHECK(cudaMemcpyToSymbol(d_timeline, &z, sizeof z));
+	if (dbuf) { cudaFree(dbuf); dbuf = nullptr; }
 	return XALM_OK;
 }
 
