@@ -45,18 +45,18 @@ for kn in configs:
     print(kn, " | ".join(res), f"launches/token {model.last_launch_count()}", flush=True)
     if os.environ.get("TIMELINE"):
         P = int(os.environ["TIMELINE"])
-        capi.timeline_start(400)
+        capi.timeline_start(800)
         model.forward_async(5, P, 1)
         model.sync()
-        tl = capi.timeline_stop(400).astype(np.int64)
+        tl = capi.timeline_stop(800).astype(np.int64)
         t0 = tl[:, 1].min()
-        names = {100: "tma_store", 101: "tma_resid", 102: "tma_glu", 103: "tma_qkv", 200: "ldg_store", 201: "ldg_resid", 202: "ldg_glu", 203: "ldg_qkv", 300: "attn"}
+        names = {400: "mega", 410: "mk_store", 411: "mk_resid", 412: "mk_glu", 413: "mk_qkv", 419: "mk_attn", 100: "tma_store", 101: "tma_resid", 102: "tma_glu", 103: "tma_qkv", 200: "ldg_store", 201: "ldg_resid", 202: "ldg_glu", 203: "ldg_qkv", 300: "attn"}
         order = np.argsort(tl[:, 1])
         prev_end = None
         rows = []
-        for i in order[: 5 * 4 + 1]:
+        for i in order[: 5 * 4 + 3]:
             kid, a, b, c = tl[i]
-            rows.append(f"  {names.get(int(kid), kid):10s} entry {(a-t0)/1e3:8.2f}us  wait_done {(b-t0)/1e3:8.2f}  exit {(c-t0)/1e3:8.2f}  | entry->wait {(b-a)/1e3:6.2f}  work {(c-b)/1e3:6.2f}" + (f"  gap_from_prev_exit {(b-prev_end)/1e3:6.2f}" if prev_end else ""))
+            rows.append(f"  {str(names.get(int(kid), kid)):10s} entry {(a-t0)/1e3:8.2f}us  wait_done {(b-t0)/1e3:8.2f}  exit {(c-t0)/1e3:8.2f}  | entry->wait {(b-a)/1e3:6.2f}  work {(c-b)/1e3:6.2f}" + (f"  gap_from_prev_exit {(b-prev_end)/1e3:6.2f}" if prev_end else ""))
             prev_end = c
         print("\n".join(rows))
         tot = (tl[:, 3].max() - t0) / 1e3

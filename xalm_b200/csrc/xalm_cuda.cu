@@ -26,6 +26,7 @@
 #include "attention.cuh"
 #include "matvec.cuh"
 #include "matvec_tma.cuh"
+#include "megakernel.cuh"
 
 namespace xalm {
 
@@ -51,6 +52,8 @@ static std::map<std::string, int>& tuning() {
 	    {"attn_splits", 0},  // 0 = auto (~2 CTAs per SM)
 	    {"attn_min_split", 128},
 	    {"mv_cfg_rows", 0},  // 0 = auto, 1 = force config A (R4 KS1 NW4), 2 = force config B (R2 KS4 NW8)
+	    {"mega", 1},         // run all layers of a token in one persistent kernel (megakernel.cuh) when the model allows
+	    {"mega_smem_kb", 200},
 	    {"tma", 1},          // stream weights with cp.async.bulk into a shared-memory ring (matvec_tma.cuh)
 	    {"tma_smem_kb", 100}, // shared-memory budget per CTA for the TMA kernel (two kernels co-reside under PDL)
 	    {"tma_rc_small", 8}, // rows per tile when the matrix has few rows (Wo, W2)
@@ -595,6 +598,14 @@ struct xalm_cuda_model {
 	int launches_per_token[2] = {0, 0};
 	int last_launches = 0;
 	ncclComm_t comm = nullptr;
+	// megakernel (megakernel.cuh)
+	bool mega = false;
+	MkPhase* d_phases = nullptr;
+	int n_phases = 0;
+	unsigned int* d_gbar = nullptr;
+	MkArgs mk_args = {};
+	size_t mk_smem = 0;
+	int mk_type = 0;
 };
 
 static int parse_tensor_name(const char* name, int n_layers, int* layer, int* piece) {
@@ -840,6 +851,116 @@ int xalm_cuda_upload_tensor(xalm_cuda_model* m, const char* name, int type_id, c
 	return XALM_OK;
 }
 
+} // extern "C" (templates below)
+
+// ---- megakernel plumbing ---------------------------------------------------------------------------------------------
+template <int TYPE>
+static cudaError_t launch_mega_typed(const MkArgs& mk, int grid, size_t smem, cudaStream_t s, bool pdl) {
+	static size_t attr_smem = 0;
+	auto kern = layer_megakernel<TYPE>;
+	if (smem > attr_smem) {
+		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
+		if (e != cudaSuccess) return e;
+		attr_smem = smem;
+	}
+	return launch_smem(kern, dim3(grid), dim3(MK_THREADS), smem, s, pdl, mk);
+}
+static cudaError_t launch_mega(int type, const MkArgs& mk, int grid, size_t smem, cudaStream_t s, bool pdl) {
+	switch (type) {
+		case XALM_F32: return launch_mega_typed<XALM_F32>(mk, grid, smem, s, pdl);
+		case XALM_F16: return launch_mega_typed<XALM_F16>(mk, grid, smem, s, pdl);
+		case XALM_BF16: return launch_mega_typed<XALM_BF16>(mk, grid, smem, s, pdl);
+		case XALM_F8_E4M3: return launch_mega_typed<XALM_F8_E4M3>(mk, grid, smem, s, pdl);
+		case XALM_F8_E5M2: return launch_mega_typed<XALM_F8_E5M2>(mk, grid, smem, s, pdl);
+		case XALM_Q8: return launch_mega_typed<XALM_Q8>(mk, grid, smem, s, pdl);
+		case XALM_Q8_0: return launch_mega_typed<XALM_Q8_0>(mk, grid, smem, s, pdl);
+		case XALM_Q4_0: return launch_mega_typed<XALM_Q4_0>(mk, grid, smem, s, pdl);
+		case XALM_Q4_1: return launch_mega_typed<XALM_Q4_1>(mk, grid, smem, s, pdl);
+		case XALM_Q5_0: return launch_mega_typed<XALM_Q5_0>(mk, grid, smem, s, pdl);
+		case XALM_Q5_1: return launch_mega_typed<XALM_Q5_1>(mk, grid, smem, s, pdl);
+	}
+	return cudaErrorInvalidValue;
+}
+static void mk_cfg_of(int type, int* KW, int* RCS, int* U) {
+	const int ppu = pieces_per_unit(type);
+	*KW = ppu == 8 ? 4 : 8;
+	*RCS = 2 * (MK_CW / *KW);
+	*U = (*KW * 32) / ppu > 0 ? (*KW * 32) / ppu : 1;
+}
+
+static void fill_layer_args(xalm_cuda_model* m, int l, MatvecArgs* qkv, AttnArgs* at, MatvecArgs* wo, MatvecArgs* w13, MatvecArgs* w2);
+
+// Decide whether the token's layers can run as one megakernel and, if so, build its phase list on the device.
+static int setup_megakernel(xalm_cuda_model* m) {
+	m->mega = false;
+	if (!tune("mega") || !tune("tma") || m->tp_size > 1) return XALM_OK;
+	const xalm_config& c = m->c;
+	const int type = m->layers[0].wqkv.m.type;
+	if (!unit_bytes(type)) return XALM_OK;
+	const int G = c.n_heads / c.n_kv_heads;
+	if ((c.head_dim != 64 && c.head_dim != 128) || (G != 1 && G != 2 && G != 4 && G != 8)) return XALM_OK;
+	int KW, RCS, U;
+	mk_cfg_of(type, &KW, &RCS, &U);
+	int max_n = 0;
+	for (auto& L : m->layers) {
+		const WMat* ws[4] = {&L.wqkv.m, &L.wo.m, &L.w13.m, &L.w2.m};
+		for (const WMat* w : ws) {
+			if (w->type != type || w->n % 256 || w->rows % RCS || (w->flags & WMAT_FP8_NONFINITE)) return XALM_OK;
+			TypeInfo ti;
+			type_info(type, &ti);
+			if (ti.block > 1 && !w->layout_units) return XALM_OK;
+			if (w->n > max_n) max_n = w->n;
+		}
+	}
+	const size_t scratch = mk_attn_scratch_floats(c.head_dim, G);
+	const size_t xb_floats = scratch > (size_t) max_n ? scratch : (size_t) max_n;
+	const int slot_bytes = RCS * U * unit_bytes(type);
+	const size_t budget = (size_t) tune("mega_smem_kb") * 1024;
+	const size_t fixed = ((xb_floats * sizeof(float) + 127) / 128) * 128 + 2 * KW * RCS * sizeof(float) + 32 * sizeof(float) + 512;
+	if (fixed + 2 * (size_t) slot_bytes > budget) return XALM_OK;
+	int NS = (int) ((budget - fixed) / slot_bytes);
+	if (NS > 16) NS = 16;
+	std::vector<MkPhase> ph;
+	for (int l = 0; l < c.n_layers; l++) {
+		MatvecArgs qkv, wo, w13, w2;
+		AttnArgs at;
+		fill_layer_args(m, l, &qkv, &at, &wo, &w13, &w2);
+		auto mv = [&](const MatvecArgs& a) {
+			MkPhase p = {};
+			p.kind = MK_MATVEC;
+			p.a = a;
+			const int vrows = a.epi == EPI_GLU ? 2 * a.d : a.d;
+			p.n_tiles = vrows / RCS;
+			p.kranges = (a.n / 256 + U - 1) / U;
+			ph.push_back(p);
+		};
+		mv(qkv);
+		MkPhase pa = {};
+		pa.kind = MK_ATTN; pa.at = at; pa.G = G; pa.HD = c.head_dim;
+		ph.push_back(pa);
+		mv(wo);
+		mv(w13);
+		mv(w2);
+	}
+	XALM_TRY(m->da.alloc((void**) &m->d_phases, ph.size() * sizeof(MkPhase)));
+	XALM_CUDA_CHECK(cudaMemcpy(m->d_phases, ph.data(), ph.size() * sizeof(MkPhase), cudaMemcpyHostToDevice));
+	XALM_TRY(m->da.alloc((void**) &m->d_gbar, 64));
+	XALM_CUDA_CHECK(cudaMemset(m->d_gbar, 0, 64));
+	m->n_phases = (int) ph.size();
+	m->mk_args.phases = m->d_phases;
+	m->mk_args.n_phases = m->n_phases;
+	m->mk_args.NS = NS;
+	m->mk_args.slot_bytes = slot_bytes;
+	m->mk_args.xb_floats = (int) xb_floats;
+	m->mk_args.gbar = m->d_gbar;
+	m->mk_smem = fixed + (size_t) NS * slot_bytes + 2 * 16 * sizeof(uint64_t);
+	m->mk_type = type;
+	m->mega = true;
+	return XALM_OK;
+}
+
+extern "C" {
+
 // ---- the per-token kernel sequence ---------------------------------------------------------------------------
 static int enqueue_token(xalm_cuda_model* m, int mode, cudaStream_t s, int* n_launches) {
 	const xalm_config& c = m->c;
@@ -851,29 +972,28 @@ static int enqueue_token(xalm_cuda_model* m, int mode, cudaStream_t s, int* n_la
 	if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "embed launch failed: %s", cudaGetErrorString(e));
 	nl++;
 	const int G = c.n_heads / c.n_kv_heads;
-	for (int l = 0; l < c.n_layers; l++) {
+	if (m->mega) {
+		XALM_CUDA_CHECK(cudaMemsetAsync(m->d_gbar, 0, sizeof(unsigned int), s));
+		e = launch_mega(m->mk_type, m->mk_args, num_sms(), m->mk_smem, s, false);
+		if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "megakernel launch failed: %s", cudaGetErrorString(e));
+		nl++;
+	}
+	for (int l = 0; l < c.n_layers && !m->mega; l++) {
 		LayerDev& L = m->layers[l];
+		MatvecArgs a_qkv, a_wo, a_w13, a_w2;
+		AttnArgs a_at;
+		fill_layer_args(m, l, &a_qkv, &a_at, &a_wo, &a_w13, &a_w2);
+		(void) L;
 		{ // attention pre-norm + q,k,v + clip + rope + KV write (+ sinks)
-			MatvecArgs a = {};
-			a.w = L.wqkv.m; a.x = m->x; a.n = c.dim; a.d = m->q_dim_l + 2 * m->kv_dim_l; a.epi = EPI_QKV;
-			a.norm_w = L.rms_att; a.norm_type = L.rms_att_type; a.norm_eps = c.norm_eps;
-			a.out = m->q; a.step = m->d_step; a.k_cache = L.k_cache; a.v_cache = L.v_cache; a.rope_freq = m->rope_freq;
-			a.q_dim = m->q_dim_l; a.kv_dim = m->kv_dim_l; a.head_dim = c.head_dim; a.qkv_clip = c.qkv_clip;
-			XALM_TRY(launch_matvec(a, s, pdl));
+			XALM_TRY(launch_matvec(a_qkv, s, pdl));
 			nl++;
 		}
 		{
-			AttnArgs a = {};
-			a.q = m->q; a.k_cache = L.k_cache; a.v_cache = L.v_cache; a.out = m->xb2; a.step = m->d_step; a.kv_len_fixed = -1;
-			a.n_kv_heads = m->n_kv_heads_l; a.n_splits = m->attn_splits; a.min_split = tune("attn_min_split");
-			a.part_acc = m->attn_acc; a.part_ml = m->attn_ml; a.tickets = m->tickets;
-			XALM_TRY(launch_attn(a, c.head_dim, G, s, pdl));
+			XALM_TRY(launch_attn(a_at, c.head_dim, G, s, pdl));
 			nl++;
 		}
 		{ // Wo + residual
-			MatvecArgs a = {};
-			a.w = L.wo.m; a.x = m->xb2; a.n = m->q_dim_l; a.d = c.dim;
-			a.epi = tp ? EPI_STORE : EPI_RESIDUAL; a.out = tp ? m->part : m->x;
+			MatvecArgs a = a_wo;
 			XALM_TRY(launch_matvec(a, s, pdl));
 			nl++;
 			if (tp) {
@@ -884,16 +1004,11 @@ static int enqueue_token(xalm_cuda_model* m, int mode, cudaStream_t s, int* n_la
 			}
 		}
 		{ // ffn pre-norm + W1,W3 + act*gate
-			MatvecArgs a = {};
-			a.w = L.w13.m; a.x = m->x; a.n = c.dim; a.d = m->hidden_l; a.epi = EPI_GLU; a.glu_off = m->hidden_l; a.act = c.act;
-			a.norm_w = L.rms_ffn; a.norm_type = L.rms_ffn_type; a.norm_eps = c.norm_eps; a.out = m->hb;
-			XALM_TRY(launch_matvec(a, s, pdl && !tp));
+			XALM_TRY(launch_matvec(a_w13, s, pdl && !tp));
 			nl++;
 		}
 		{ // W2 + residual
-			MatvecArgs a = {};
-			a.w = L.w2.m; a.x = m->hb; a.n = m->hidden_l; a.d = c.dim;
-			a.epi = tp ? EPI_STORE : EPI_RESIDUAL; a.out = tp ? m->part : m->x;
+			MatvecArgs a = a_w2;
 			XALM_TRY(launch_matvec(a, s, pdl));
 			nl++;
 			if (tp) {
@@ -918,6 +1033,47 @@ static int enqueue_token(xalm_cuda_model* m, int mode, cudaStream_t s, int* n_la
 	if (n_launches) *n_launches = nl;
 	return XALM_OK;
 }
+
+} // extern "C"
+static void fill_layer_args(xalm_cuda_model* m, int l, MatvecArgs* qkv, AttnArgs* at, MatvecArgs* wo, MatvecArgs* w13, MatvecArgs* w2) {
+	const xalm_config& c = m->c;
+	LayerDev& L = m->layers[l];
+	const bool tp = m->tp_size > 1;
+	{ // attention pre-norm + q,k,v + clip + rope + KV write (+ sinks)
+		MatvecArgs a = {};
+		a.w = L.wqkv.m; a.x = m->x; a.n = c.dim; a.d = m->q_dim_l + 2 * m->kv_dim_l; a.epi = EPI_QKV;
+		a.norm_w = L.rms_att; a.norm_type = L.rms_att_type; a.norm_eps = c.norm_eps;
+		a.out = m->q; a.step = m->d_step; a.k_cache = L.k_cache; a.v_cache = L.v_cache; a.rope_freq = m->rope_freq;
+		a.q_dim = m->q_dim_l; a.kv_dim = m->kv_dim_l; a.head_dim = c.head_dim; a.qkv_clip = c.qkv_clip;
+		*qkv = a;
+	}
+	{
+		AttnArgs a = {};
+		a.q = m->q; a.k_cache = L.k_cache; a.v_cache = L.v_cache; a.out = m->xb2; a.step = m->d_step; a.kv_len_fixed = -1;
+		a.n_kv_heads = m->n_kv_heads_l; a.n_splits = m->attn_splits; a.min_split = tune("attn_min_split");
+		a.part_acc = m->attn_acc; a.part_ml = m->attn_ml; a.tickets = m->tickets;
+		*at = a;
+	}
+	{ // Wo + residual
+		MatvecArgs a = {};
+		a.w = L.wo.m; a.x = m->xb2; a.n = m->q_dim_l; a.d = c.dim;
+		a.epi = tp ? EPI_STORE : EPI_RESIDUAL; a.out = tp ? m->part : m->x;
+		*wo = a;
+	}
+	{ // ffn pre-norm + W1,W3 + act*gate
+		MatvecArgs a = {};
+		a.w = L.w13.m; a.x = m->x; a.n = c.dim; a.d = m->hidden_l; a.epi = EPI_GLU; a.glu_off = m->hidden_l; a.act = c.act;
+		a.norm_w = L.rms_ffn; a.norm_type = L.rms_ffn_type; a.norm_eps = c.norm_eps; a.out = m->hb;
+		*w13 = a;
+	}
+	{ // W2 + residual
+		MatvecArgs a = {};
+		a.w = L.w2.m; a.x = m->hb; a.n = m->hidden_l; a.d = c.dim;
+		a.epi = tp ? EPI_STORE : EPI_RESIDUAL; a.out = tp ? m->part : m->x;
+		*w2 = a;
+	}
+}
+extern "C" {
 
 int xalm_cuda_finalize(xalm_cuda_model* m) {
 	if (!m) return set_error(XALM_ERR_INVALID, "model is NULL");
@@ -966,6 +1122,7 @@ int xalm_cuda_finalize(xalm_cuda_model* m) {
 	XALM_TRY(m->da.alloc((void**) &m->d_step, sizeof(StepParams)));
 	XALM_CUDA_CHECK(cudaMallocHost((void**) &m->h_step, 64 * sizeof(StepParams)));
 	XALM_CUDA_CHECK(cudaMallocHost((void**) &m->h_logits, (size_t) c.vocab_size * sizeof(float)));
+	XALM_TRY(setup_megakernel(m));
 	XALM_CUDA_CHECK(cudaDeviceSynchronize());
 	m->finalized = true;
 	return XALM_OK;
