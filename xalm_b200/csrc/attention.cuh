@@ -90,17 +90,28 @@ __global__ void __launch_bounds__(NW * 32) attn_decode_kernel(const AttnArgs a) 
 	const __half* kbase = a.k_cache + (size_t) kvh * HD + li * 8;
 	const __half* vbase = a.v_cache + (size_t) kvh * HD + li * 8;
 
-	for (int tb = t0 + warp * RPW * TB; tb < t1; tb += NW * RPW * TB) {
+	uint4 kn[TB], vn[TB]; // next batch, requested one iteration ahead
+	auto fetch = [&](int tb) {
+#pragma unroll
+		for (int j = 0; j < TB; j++) {
+			const int t = tb + j * RPW + sub;
+			const int tc = t < t1 ? t : t0;
+			kn[j] = ld_stream16(kbase + (size_t) tc * kv_stride);
+			vn[j] = ld_stream16(vbase + (size_t) tc * kv_stride);
+		}
+	};
+	const int tb_first = t0 + warp * RPW * TB;
+	if (tb_first < t1) fetch(tb_first);
+	for (int tb = tb_first; tb < t1; tb += NW * RPW * TB) {
 		uint4 kq[TB], vq[TB];
 		bool ok[TB];
 #pragma unroll
 		for (int j = 0; j < TB; j++) {
-			const int t = tb + j * RPW + sub;
-			ok[j] = t < t1;
-			const int tc = ok[j] ? t : t0;
-			kq[j] = ld_stream16(kbase + (size_t) tc * kv_stride);
-			vq[j] = ld_stream16(vbase + (size_t) tc * kv_stride);
+			ok[j] = tb + j * RPW + sub < t1;
+			kq[j] = kn[j];
+			vq[j] = vn[j];
 		}
+		if (tb + NW * RPW * TB < t1) fetch(tb + NW * RPW * TB);
 		float s[TB][G];
 #pragma unroll
 		for (int j = 0; j < TB; j++) {
@@ -181,6 +192,19 @@ __global__ void __launch_bounds__(NW * 32) attn_decode_kernel(const AttnArgs a) 
 	__syncthreads();
 	float* pacc = a.part_acc + ((size_t) kvh * a.n_splits + split) * G * HD;
 	float* pml = a.part_ml + ((size_t) kvh * a.n_splits + split) * G * 2;
+	if (n_active == 1) {
+		// the whole sequence fit in one split: normalise and write the output directly (no partial round trip, no ticket)
+		for (int i = threadIdx.x; i < G * HD; i += NW * 32) {
+			const int g = i / HD, dpos = i % HD;
+			float v = 0.f, L = 0.f;
+#pragma unroll
+			for (int w = 0; w < NW; w++) v += s_acc[w][g][dpos];
+			for (int k = 0; k < NGRP; k++) L += s_l[k][g] * s_scale[k][g];
+			a.out[(size_t) kvh * G * HD + i] = v / L;
+		}
+		tl_mark(tl, 3);
+		return;
+	}
 	for (int i = threadIdx.x; i < G * HD; i += NW * 32) {
 		const int g = i / HD, dpos = i % HD;
 		float v = 0.f;
@@ -213,18 +237,38 @@ __global__ void __launch_bounds__(NW * 32) attn_decode_kernel(const AttnArgs a) 
 	__threadfence();
 	const float* bacc = a.part_acc + (size_t) kvh * a.n_splits * G * HD;
 	const float* bml = a.part_ml + (size_t) kvh * a.n_splits * G * 2;
+	// (m, l) of every split -> shared memory (reusing s_acc), then per-head max, rescale factors and denominators
+	float* s_ml = &s_acc[0][0][0];                 // [n_active][G][2]   (n_active * G * 2 <= NW * G * HD)
+	float* s_sc = s_ml + (size_t) n_active * G * 2; // [n_active][G]
+	for (int i = threadIdx.x; i < n_active * G * 2; i += NW * 32) s_ml[i] = __ldcg(bml + i);
+	__syncthreads();
+	__shared__ float s_den[G];
+	if (threadIdx.x < G) {
+		const int g = threadIdx.x;
+		float mm = -CUDART_INF_F;
+		for (int sidx = 0; sidx < n_active; sidx++) mm = fmaxf(mm, s_ml[(sidx * G + g) * 2]);
+		float den = 0.f;
+		for (int sidx = 0; sidx < n_active; sidx++) {
+			const float sc = expf(s_ml[(sidx * G + g) * 2] - mm);
+			s_sc[sidx * G + g] = sc;
+			den += sc * s_ml[(sidx * G + g) * 2 + 1];
+		}
+		s_den[g] = den;
+	}
+	__syncthreads();
 	for (int i = threadIdx.x; i < G * HD; i += NW * 32) {
 		const int g = i / HD;
-		float mm = -CUDART_INF_F;
-		for (int sidx = 0; sidx < n_active; sidx++) mm = fmaxf(mm, __ldcg(bml + ((size_t) sidx * G + g) * 2));
-		float num = 0.f, den = 0.f;
-		for (int sidx = 0; sidx < n_active; sidx++) {
-			const float ms = __ldcg(bml + ((size_t) sidx * G + g) * 2), ls = __ldcg(bml + ((size_t) sidx * G + g) * 2 + 1);
-			const float sc = expf(ms - mm);
-			num += sc * __ldcg(bacc + (size_t) sidx * G * HD + i);
-			den += sc * ls;
+		float num = 0.f;
+		int sidx = 0;
+		for (; sidx + 8 <= n_active; sidx += 8) { // 8 independent L2 loads in flight per thread
+			float v[8];
+#pragma unroll
+			for (int k = 0; k < 8; k++) v[k] = __ldcg(bacc + (size_t) (sidx + k) * G * HD + i);
+#pragma unroll
+			for (int k = 0; k < 8; k++) num += s_sc[(sidx + k) * G + g] * v[k];
 		}
-		a.out[(size_t) kvh * G * HD + i] = num / den;
+		for (; sidx < n_active; sidx++) num += s_sc[sidx * G + g] * __ldcg(bacc + (size_t) sidx * G * HD + i);
+		a.out[(size_t) kvh * G * HD + i] = num / s_den[g];
 	}
 }
 

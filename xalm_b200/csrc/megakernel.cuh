@@ -269,34 +269,50 @@ __host__ __device__ inline size_t mk_attn_scratch_floats(int HD, int G) {
 struct MkArgs {
 	const MkPhase* phases;
 	int n_phases;
-	int NS;               // ring slots
-	int slot_bytes;       // bytes per slot (>= RCS * U * UB)
+	int NS;               // ring slots PER consumer group
+	int slot_bytes;       // bytes per slot (>= 8 rows * U * UB)
 	int xb_floats;        // activation staging area (max n over phases, and >= attention scratch)
 	unsigned int* gbar;   // grid barrier counter, zero at launch
 };
 
+constexpr int MK_GROUPS = 2;              // independent 8-warp consumer groups per CTA (each with its own ring + producer warp)
+constexpr int MK_GW = MK_CW / MK_GROUPS;  // warps per group
+constexpr int MK_THREADS2 = (MK_CW + MK_GROUPS) * 32;
+
 template <int TYPE>
-__global__ void __launch_bounds__(MK_THREADS, 1) layer_megakernel(const MkArgs mk) {
+struct MkCfg2 {
+	static constexpr int PPU = UFmt<TYPE>::PPU;
+	static constexpr int KW = PPU == 8 ? 4 : 8;   // K-slice warps per group
+	static constexpr int RW = MK_GW / KW;         // row groups
+	static constexpr int RC = 8;                  // rows per full tile
+	static constexpr int R = RC / RW;             // rows per warp
+	static constexpr int U = (KW * 32) / PPU > 0 ? (KW * 32) / PPU : 1; // units per stage (one piece per lane per row)
+};
+
+__device__ __forceinline__ void mk_group_bar(int group) { asm volatile("bar.sync %0, 256;" ::"r"(2 + group) : "memory"); }
+
+template <int TYPE>
+__global__ void __launch_bounds__(MK_THREADS2, 1) layer_megakernel(const MkArgs mk) {
 	using F = Fmt<TYPE>;
 	using UF = UFmt<TYPE>;
-	using C = MkCfg<TYPE>;
-	constexpr int E = F::E, PPU = C::PPU, KW = C::KW, RCS = C::RCS, U = C::U;
+	using C = MkCfg2<TYPE>;
+	constexpr int E = F::E, PPU = C::PPU, KW = C::KW, RC = C::RC, R = C::R, U = C::U;
 	const int UB = unit_bytes(TYPE);
 	const int NS = mk.NS;
 
 	extern __shared__ __align__(128) uint8_t smem[];
 	float* xb = reinterpret_cast<float*>(smem);
-	uint8_t* ring = smem + (((size_t) mk.xb_floats * sizeof(float) + 127) / 128) * 128;
-	float* part = reinterpret_cast<float*>(ring + (size_t) NS * mk.slot_bytes); // [2][KW][RCS]
-	float* s_red = part + 2 * KW * RCS;                                          // [MK_CW]
-	uint64_t* full = reinterpret_cast<uint64_t*>(s_red + 32);
-	uint64_t* empty = full + NS;
+	uint8_t* ring0 = smem + (((size_t) mk.xb_floats * sizeof(float) + 127) / 128) * 128;
+	float* part0 = reinterpret_cast<float*>(ring0 + (size_t) MK_GROUPS * NS * mk.slot_bytes); // [group][2][KW][RC]
+	float* s_red = part0 + MK_GROUPS * 2 * KW * RC;                                            // [MK_CW]
+	uint64_t* full0 = reinterpret_cast<uint64_t*>(s_red + 32);                                 // [group][NS]
+	uint64_t* empty0 = full0 + MK_GROUPS * NS;
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	if (threadIdx.x == 0) {
-		for (int s = 0; s < NS; s++) {
-			mbar_init(&full[s], 1);
-			mbar_init(&empty[s], MK_CW);
+		for (int s = 0; s < MK_GROUPS * NS; s++) {
+			mbar_init(&full0[s], 1);
+			mbar_init(&empty0[s], MK_GW);
 		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
@@ -304,28 +320,40 @@ __global__ void __launch_bounds__(MK_THREADS, 1) layer_megakernel(const MkArgs m
 	pdl_launch_dependents();
 	int tl = -1;
 	if (blockIdx.x == 0 && threadIdx.x == 0) tl = tl_begin(400);
+	const int n_vcta = (int) gridDim.x * MK_GROUPS; // "virtual CTAs" = consumer groups
 
-	if (warp == MK_CW) {
-		// ===================== producer: the whole token's weight stream, never blocked by a grid barrier =====================
+	if (warp >= MK_CW) {
+		// ===================== producers (one per group): the whole token's weight stream, never blocked by a grid barrier =====
+		const int group = warp - MK_CW;
 		if (lane == 0) {
+			uint8_t* ring = ring0 + (size_t) group * NS * mk.slot_bytes;
+			uint64_t* full = full0 + group * NS;
+			uint64_t* empty = empty0 + group * NS;
+			const int v = (int) blockIdx.x * MK_GROUPS + group;
 			int slot = 0, phase = 0;
 			for (int ph = 0; ph < mk.n_phases; ph++) {
 				const MkPhase& P = mk.phases[ph];
 				if (P.kind != MK_MATVEC) continue;
-				const int nu = P.a.n / 256, n_tiles = P.n_tiles, kranges = P.kranges;
-				for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-					const int row0 = tile * RCS;
+				const int nu = P.a.n / 256, n_tiles = P.n_tiles, kranges = P.kranges, rc = P.pad;
+				const int epi = P.a.epi, glu_off = P.a.glu_off;
+				const uint8_t* w0 = P.a.w.p0;
+				const size_t ws = P.a.w.s0;
+				for (int tile = v; tile < n_tiles; tile += n_vcta) {
+					const int row0 = tile * rc;
 					for (int kr = 0; kr < kranges; kr++) {
 						mbar_wait(&empty[slot], phase ^ 1);
 						const int u0 = kr * U;
 						const int un = min(U, nu - u0);
 						const uint32_t bytes = (uint32_t) un * UB;
-						mbar_expect_tx(&full[slot], bytes * RCS);
+						mbar_expect_tx(&full[slot], bytes * rc);
 						uint8_t* dst = ring + (size_t) slot * mk.slot_bytes;
-#pragma unroll
-						for (int r = 0; r < RCS; r++) {
-							const int pr = mk_phys_row(P.a, row0, r);
-							bulk_g2s(dst + (size_t) r * U * UB, P.a.w.p0 + (size_t) pr * P.a.w.s0 + (size_t) u0 * UB, bytes, &full[slot]);
+						for (int r = 0; r < rc; r++) {
+							int pr = row0 + r;
+							if (epi == EPI_GLU) { // interleave: even r -> W1[o], odd r -> W3[o]
+								const int o = (row0 >> 1) + (r >> 1);
+								pr = (r & 1) ? glu_off + o : o;
+							}
+							bulk_g2s(dst + (size_t) r * U * UB, w0 + (size_t) pr * ws + (size_t) u0 * UB, bytes, &full[slot]);
 						}
 						if (++slot == NS) { slot = 0; phase ^= 1; }
 					}
@@ -338,9 +366,15 @@ __global__ void __launch_bounds__(MK_THREADS, 1) layer_megakernel(const MkArgs m
 	// ===================== consumers =====================
 	pdl_wait();
 	tl_mark(tl, 2);
-	const int kw = warp % KW, rw = warp / KW;
+	const int group = warp / MK_GW, gwarp = warp % MK_GW;
+	const int kw = gwarp % KW, rw = gwarp / KW;
 	const int my_piece = kw * 32 + lane; // piece index inside a stage row
 	const int pu = my_piece / PPU, pp = my_piece % PPU;
+	uint8_t* ring = ring0 + (size_t) group * NS * mk.slot_bytes;
+	uint64_t* full = full0 + group * NS;
+	uint64_t* empty = empty0 + group * NS;
+	float* part = part0 + group * 2 * KW * RC;
+	const int v = (int) blockIdx.x * MK_GROUPS + group;
 	int slot = 0, phase = 0;
 
 	for (int ph = 0; ph < mk.n_phases; ph++) {
@@ -354,25 +388,28 @@ __global__ void __launch_bounds__(MK_THREADS, 1) layer_megakernel(const MkArgs m
 		if (ph > 0) mk_grid_barrier(mk.gbar, (unsigned int) ph * gridDim.x);
 		tl_mark(tlp, 2);
 		if (P.kind == MK_ATTN) {
+#ifndef XALM_MK_NO_ATTN
 			switch (P.G) {
 				case 1: mk_attention_hd<1>(P.at, P.HD, xb); break;
 				case 2: mk_attention_hd<2>(P.at, P.HD, xb); break;
 				case 4: mk_attention_hd<4>(P.at, P.HD, xb); break;
 				case 8: mk_attention_hd<8>(P.at, P.HD, xb); break;
 			}
+#endif
 			tl_mark(tlp, 3);
 			continue;
 		}
 		const MatvecArgs& a = P.a;
-		const int n = a.n, nu = n / 256;
-		if (a.epi == EPI_QKV && blockIdx.x == 0 && a.step->kv_sink > 0) {
+		const int n = a.n, nu = n / 256, epi = a.epi, rc = P.pad;
+		float* const out = a.out;
+		if (epi == EPI_QKV && blockIdx.x == 0 && a.step->kv_sink > 0) {
 			const int pairs = a.kv_dim / 2;
 			for (int i = threadIdx.x; i < a.step->kv_sink * pairs; i += MK_CW * 32) {
 				const int r = i / pairs, p = i % pairs;
 				__half2* kp = reinterpret_cast<__half2*>(a.k_cache + (size_t) r * a.kv_dim) + p;
-				float2 v = __half22float2(__ldcg(kp));
-				rope_pair(v.x, v.y, (2 * p) % a.head_dim, 1, a.rope_freq);
-				*kp = __floats2half2_rn(v.x, v.y);
+				float2 vv = __half22float2(__ldcg(kp));
+				rope_pair(vv.x, vv.y, (2 * p) % a.head_dim, 1, a.rope_freq);
+				*kp = __floats2half2_rn(vv.x, vv.y);
 			}
 		}
 		// ---- stage activations (L2 loads: other SMs wrote them in the previous phase), permuted per unit ----
@@ -385,9 +422,9 @@ __global__ void __launch_bounds__(MK_THREADS, 1) layer_megakernel(const MkArgs m
 			const bool norm = a.norm_w != nullptr;
 			float ss = 0.f;
 			for (int i = threadIdx.x * 4; i < n; i += MK_CW * 32 * 4) {
-				const float4 v = ld_cg4(a.x + i);
-				*reinterpret_cast<float4*>(xb + xpos(i)) = v;
-				ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+				const float4 xvv = ld_cg4(a.x + i);
+				*reinterpret_cast<float4*>(xb + xpos(i)) = xvv;
+				ss += xvv.x * xvv.x + xvv.y * xvv.y + xvv.z * xvv.z + xvv.w * xvv.w;
 			}
 			if (norm) {
 				ss = warp_sum(ss);
@@ -398,7 +435,7 @@ __global__ void __launch_bounds__(MK_THREADS, 1) layer_megakernel(const MkArgs m
 				for (int i = 0; i < MK_CW; i++) tot += s_red[i];
 				const float scale = 1.0f / sqrtf(tot / (float) n + a.norm_eps);
 				for (int i = threadIdx.x * 4; i < n; i += MK_CW * 32 * 4) {
-					float4 v = *reinterpret_cast<float4*>(xb + xpos(i));
+					float4 xvv = *reinterpret_cast<float4*>(xb + xpos(i));
 					float4 g;
 					if (a.norm_type == XALM_F32) g = ld_act4(reinterpret_cast<const float*>(a.norm_w) + i);
 					else {
@@ -406,8 +443,8 @@ __global__ void __launch_bounds__(MK_THREADS, 1) layer_megakernel(const MkArgs m
 						g = make_float4(__uint_as_float(gv.x << 16), __uint_as_float(gv.x & 0xFFFF0000u), __uint_as_float(gv.y << 16),
 						                __uint_as_float(gv.y & 0xFFFF0000u));
 					}
-					v.x = v.x * scale * g.x; v.y = v.y * scale * g.y; v.z = v.z * scale * g.z; v.w = v.w * scale * g.w; // infer.cpp:233-235
-					*reinterpret_cast<float4*>(xb + xpos(i)) = v;
+					xvv.x = xvv.x * scale * g.x; xvv.y = xvv.y * scale * g.y; xvv.z = xvv.z * scale * g.z; xvv.w = xvv.w * scale * g.w; // infer.cpp:233-235
+					*reinterpret_cast<float4*>(xb + xpos(i)) = xvv;
 				}
 			}
 			mk_bar_sync_all();
@@ -418,63 +455,73 @@ __global__ void __launch_bounds__(MK_THREADS, 1) layer_megakernel(const MkArgs m
 			const float* xs = xb + (size_t) (u0 + pu) * 256 + pp * 4;
 #pragma unroll
 			for (int i = 0; i < E; i += 4) {
-				const float4 v = *reinterpret_cast<const float4*>(xs + i * PPU);
-				xv[i] = v.x; xv[i + 1] = v.y; xv[i + 2] = v.z; xv[i + 3] = v.w;
+				const float4 t4 = *reinterpret_cast<const float4*>(xs + i * PPU);
+				xv[i] = t4.x; xv[i + 1] = t4.y; xv[i + 2] = t4.z; xv[i + 3] = t4.w;
 			}
 		};
 		const int kranges = P.kranges, n_tiles = P.n_tiles;
 		const bool single_range = kranges == 1;
-		const bool lane_live0 = pu < nu; // short rows: lanes beyond the row idle
-		if (single_range && lane_live0) load_xv(0);
+		if (single_range && pu < nu) load_xv(0);
+		const int rrows = rc / C::RW; // rows this warp handles per tile (R for full tiles, R/2 for 4-row tiles)
 
 		int tcount = 0;
-		for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tcount++) {
-			f32x2 acc0 = pack2(0.f, 0.f), acc1 = pack2(0.f, 0.f);
+		for (int tile = v; tile < n_tiles; tile += n_vcta, tcount++) {
+			const int row0 = tile * rc;
+			const bool reducer = kw == (tcount % KW) && rw == 0;
+			// residual: fetch the old activation early so the epilogue does not sit on an L2 round trip
+			float xold = 0.f;
+			if (epi == EPI_RESIDUAL && reducer && lane < rc) xold = __ldcg(out + row0 + lane);
+			f32x2 acc[R];
+#pragma unroll
+			for (int r = 0; r < R; r++) acc[r] = pack2(0.f, 0.f);
 			for (int kr = 0; kr < kranges; kr++) {
 				const int u0 = kr * U;
 				const bool live = u0 + pu < nu;
 				mbar_wait(&full[slot], phase);
 				if (live) {
 					if (!single_range) load_xv(u0);
-					const uint8_t* rows = ring + (size_t) slot * mk.slot_bytes + (size_t) (rw * 2) * U * UB + (size_t) pu * UB;
-					const typename F::Frag f0 = UF::load(rows, pp);
-					const typename F::Frag f1 = UF::load(rows + (size_t) U * UB, pp);
-					F::fma_chunk(f0, xv, acc0);
-					F::fma_chunk(f1, xv, acc1);
+					const uint8_t* rows = ring + (size_t) slot * mk.slot_bytes + (size_t) (rw * rrows) * U * UB + (size_t) pu * UB;
+#pragma unroll
+					for (int r = 0; r < R; r++) {
+						if (r < rrows) {
+							const typename F::Frag f = UF::load(rows + (size_t) r * U * UB, pp);
+							F::fma_chunk(f, xv, acc[r]);
+						}
+					}
 				}
 				__syncwarp();
 				if (lane == 0) mbar_arrive(&empty[slot]);
 				if (++slot == NS) { slot = 0; phase ^= 1; }
 			}
-			// ---- two rows x 32 lanes -> two sums with 5 shuffles (transpose-reduce), then across the KW K-slice warps ----
-			float lo0, hi0, lo1, hi1;
-			unpack2(acc0, lo0, hi0);
-			unpack2(acc1, lo1, hi1);
-			const float s0 = lo0 + hi0, s1 = lo1 + hi1;
-			const bool upper = lane >= 16;
-			float v = (upper ? s1 : s0) + __shfl_xor_sync(0xffffffffu, upper ? s0 : s1, 16); // lanes 0-15: row 0, lanes 16-31: row 1
+			// ---- lanes -> one sum per row; K-slice warps -> shared memory (fixed order) ----
+			float* pt = part + (tcount & 1) * (KW * RC);
 #pragma unroll
-			for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-			float* pt = part + (tcount & 1) * (KW * RCS);
-			if ((lane & 15) == 0) pt[kw * RCS + rw * 2 + (lane >> 4)] = v;
-			mk_bar_sync_group(rw, KW * 32);
-			if (kw == (tcount % KW) && lane == 0) { // rotating reducer, fixed summation order
-				float y2[2] = {0.f, 0.f};
+			for (int r = 0; r < R; r++) {
+				float lo, hi;
+				unpack2(acc[r], lo, hi);
+				const float y = warp_sum(lo + hi);
+				if (lane == 0 && r < rrows) pt[kw * RC + rw * rrows + r] = y;
+			}
+			mk_group_bar(group);
+			if (reducer) { // rotating reducer warp: lane i owns row i of the tile
+				float yv = 0.f;
+				if (lane < rc) {
 #pragma unroll
-				for (int k = 0; k < KW; k++) {
-					y2[0] += pt[k * RCS + rw * 2];
-					y2[1] += pt[k * RCS + rw * 2 + 1];
+					for (int k = 0; k < KW; k++) yv += pt[k * RC + lane];
 				}
-				const int row0 = tile * RCS + rw * 2;
-				if (a.epi == EPI_GLU) {
-					const int o = row0 >> 1;
-					const float g = a.act == XALM_SILU ? act_silu(y2[0]) : act_gelu(y2[0]);
-					a.out[o] = g * y2[1];
-				} else if (a.epi == EPI_RESIDUAL) {
-					a.out[row0] = __ldcg(a.out + row0) + y2[0];
-					a.out[row0 + 1] = __ldcg(a.out + row0 + 1) + y2[1];
-				} else {
-					epilogue<2>(a, row0, y2);
+				const float ynext = __shfl_down_sync(0xffffffffu, yv, 1);
+				if (lane < rc) {
+					if (epi == EPI_RESIDUAL) {
+						out[row0 + lane] = xold + yv;
+					} else if (epi == EPI_GLU) {
+						if ((lane & 1) == 0) { // (W1[o], W3[o]) sit in adjacent rows of a GLU tile
+							const float g = a.act == XALM_SILU ? act_silu(yv) : act_gelu(yv);
+							out[(row0 + lane) >> 1] = g * ynext;
+						}
+					} else if ((lane & 1) == 0) {
+						const float y2[2] = {yv, ynext};
+						epilogue<2>(a, row0 + lane, y2);
+					}
 				}
 			}
 		}

@@ -49,11 +49,12 @@ static std::map<std::string, int>& tuning() {
 	static std::map<std::string, int> t = {
 	    {"pdl", 1},          // programmatic dependent launch between the kernels of a token
 	    {"graph", 1},        // replay a captured CUDA graph per token
-	    {"attn_splits", 0},  // 0 = auto (~2 CTAs per SM)
+	    {"attn_splits", 0},  // 0 = auto (~1 CTA per SM, at most 32 splits per kv head)
 	    {"attn_min_split", 128},
 	    {"mv_cfg_rows", 0},  // 0 = auto, 1 = force config A (R4 KS1 NW4), 2 = force config B (R2 KS4 NW8)
-	    {"mega", 1},         // run all layers of a token in one persistent kernel (megakernel.cuh) when the model allows
+	    {"mega", 0},         // EXPERIMENTAL (not faster yet): run all layers of a token in one persistent kernel (megakernel.cuh) when the model allows
 	    {"mega_smem_kb", 200},
+	    {"mega_rc_small", 4},
 	    {"tma", 1},          // stream weights with cp.async.bulk into a shared-memory ring (matvec_tma.cuh)
 	    {"tma_smem_kb", 100}, // shared-memory budget per CTA for the TMA kernel (two kernels co-reside under PDL)
 	    {"tma_rc_small", 8}, // rows per tile when the matrix has few rows (Wo, W2)
@@ -377,12 +378,13 @@ static std::vector<float> rope_freq_table(int head_dim, int rotary_dim, float th
 // ---------------------------------------------------------------------------------------------------------
 template <int HD>
 static cudaError_t launch_attn_hd(const AttnArgs& a, int G, cudaStream_t s, bool pdl) {
-	dim3 grid(a.n_splits, a.n_kv_heads), block(128);
+	dim3 grid(a.n_splits, a.n_kv_heads), block(256);
+	constexpr int NW8 = HD >= 256 ? 4 : 8; // 8 query heads x 256 dims: keep the per-warp partials within 48 KB of static smem
 	switch (G) {
-		case 1: return launch(attn_decode_kernel<HD, 1, 4>, grid, block, s, pdl, a);
-		case 2: return launch(attn_decode_kernel<HD, 2, 4>, grid, block, s, pdl, a);
-		case 4: return launch(attn_decode_kernel<HD, 4, 4>, grid, block, s, pdl, a);
-		case 8: return launch(attn_decode_kernel<HD, 8, 4>, grid, block, s, pdl, a);
+		case 1: return launch(attn_decode_kernel<HD, 1, 8>, grid, block, s, pdl, a);
+		case 2: return launch(attn_decode_kernel<HD, 2, 8>, grid, block, s, pdl, a);
+		case 4: return launch(attn_decode_kernel<HD, 4, 8>, grid, block, s, pdl, a);
+		case 8: return launch(attn_decode_kernel<HD, 8, NW8>, grid, dim3(NW8 * 32), s, pdl, a);
 	}
 	return cudaErrorInvalidValue;
 }
@@ -406,7 +408,9 @@ static int attn_auto_splits(int n_kv_heads) {
 	int sms = 148;
 	int dev = 0;
 	if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-	int s = (2 * sms + n_kv_heads - 1) / n_kv_heads;
+	// about one CTA per SM, and never so many splits that the last-CTA merge dominates (measured: profiles/r1_attention_splits.md)
+	int s = sms / n_kv_heads;
+	if (s > 32) s = 32;
 	return s < 1 ? 1 : s;
 }
 
@@ -863,7 +867,7 @@ static cudaError_t launch_mega_typed(const MkArgs& mk, int grid, size_t smem, cu
 		if (e != cudaSuccess) return e;
 		attr_smem = smem;
 	}
-	return launch_smem(kern, dim3(grid), dim3(MK_THREADS), smem, s, pdl, mk);
+	return launch_smem(kern, dim3(grid), dim3(MK_THREADS2), smem, s, pdl, mk);
 }
 static cudaError_t launch_mega(int type, const MkArgs& mk, int grid, size_t smem, cudaStream_t s, bool pdl) {
 	switch (type) {
@@ -884,7 +888,7 @@ static cudaError_t launch_mega(int type, const MkArgs& mk, int grid, size_t smem
 static void mk_cfg_of(int type, int* KW, int* RCS, int* U) {
 	const int ppu = pieces_per_unit(type);
 	*KW = ppu == 8 ? 4 : 8;
-	*RCS = 2 * (MK_CW / *KW);
+	*RCS = 8;
 	*U = (*KW * 32) / ppu > 0 ? (*KW * 32) / ppu : 1;
 }
 
@@ -916,10 +920,10 @@ static int setup_megakernel(xalm_cuda_model* m) {
 	const size_t xb_floats = scratch > (size_t) max_n ? scratch : (size_t) max_n;
 	const int slot_bytes = RCS * U * unit_bytes(type);
 	const size_t budget = (size_t) tune("mega_smem_kb") * 1024;
-	const size_t fixed = ((xb_floats * sizeof(float) + 127) / 128) * 128 + 2 * KW * RCS * sizeof(float) + 32 * sizeof(float) + 512;
-	if (fixed + 2 * (size_t) slot_bytes > budget) return XALM_OK;
-	int NS = (int) ((budget - fixed) / slot_bytes);
-	if (NS > 16) NS = 16;
+	const size_t fixed = ((xb_floats * sizeof(float) + 127) / 128) * 128 + MK_GROUPS * 2 * KW * RCS * sizeof(float) + 32 * sizeof(float) + 512;
+	if (fixed + 2 * MK_GROUPS * (size_t) slot_bytes > budget) return XALM_OK;
+	int NS = (int) ((budget - fixed) / slot_bytes / MK_GROUPS); // ring slots per consumer group
+	if (NS > 8) NS = 8;
 	std::vector<MkPhase> ph;
 	for (int l = 0; l < c.n_layers; l++) {
 		MatvecArgs qkv, wo, w13, w2;
@@ -930,7 +934,12 @@ static int setup_megakernel(xalm_cuda_model* m) {
 			p.kind = MK_MATVEC;
 			p.a = a;
 			const int vrows = a.epi == EPI_GLU ? 2 * a.d : a.d;
-			p.n_tiles = vrows / RCS;
+			// rows per tile: 8, or 4 when 8-row tiles would leave the consumer groups badly balanced (Wo, W2)
+			int rc = RCS;
+			const int groups = num_sms() * MK_GROUPS;
+			if (tune("mega_rc_small") == 4 && vrows / 8 < 4 * groups && KW == 8) rc = 4;
+			p.pad = rc;
+			p.n_tiles = vrows / rc;
 			p.kranges = (a.n / 256 + U - 1) / U;
 			ph.push_back(p);
 		};
@@ -953,7 +962,7 @@ static int setup_megakernel(xalm_cuda_model* m) {
 	m->mk_args.slot_bytes = slot_bytes;
 	m->mk_args.xb_floats = (int) xb_floats;
 	m->mk_args.gbar = m->d_gbar;
-	m->mk_smem = fixed + (size_t) NS * slot_bytes + 2 * 16 * sizeof(uint64_t);
+	m->mk_smem = fixed + (size_t) MK_GROUPS * NS * slot_bytes + 2 * MK_GROUPS * 8 * sizeof(uint64_t);
 	m->mk_type = type;
 	m->mega = true;
 	return XALM_OK;
