@@ -1,0 +1,115 @@
+"""Tensor-parallel plan on the CPU: world_size 2 over gloo.  Each rank runs the ORACLE ops on its shard, the two
+exchanges of a layer are all_reduce(sum); the result must match the unsharded oracle (fp32 reassociation noise only)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import oracle  # noqa: E402
+from xalm_b200 import synth, tp  # noqa: E402
+from xalm_b200 import types as T  # noqa: E402
+from xalm_b200 import xalm_file as X  # noqa: E402
+
+
+def _layer_tp(rank, size, cfg, tensors, x, pos, out_q):
+    """One transformer layer at position `pos` (empty cache: kv_len = 1) with the TP plan, through oracle ops."""
+    t = {n: (ty, raw) for n, ty, raw in tensors}
+    shapes = X.expected_tensors(cfg)
+    def shard(name):
+        ty, raw = t[name]
+        rows, cols = tp.shard_ranges(name, cfg, rank, size)
+        return ty, tp.slice_raw(ty, shapes[name], raw, rows, cols)
+    dim, hd = cfg["dim"], cfg["head_dim"]
+    nh, nkv, hid = cfg["n_heads"] // size, cfg["n_kv_heads"] // size, cfg["hidden_dim"] // size
+    ty, g = t["l.0.attn.norm.weight"]
+    xb = oracle.rmsnorm(x, g, ty.id, cfg["norm_eps"])
+    ty, w = shard("l.0.attn.q.weight"); q = oracle.matmul(xb, w, ty.id, dim, nh * hd, 2)
+    ty, w = shard("l.0.attn.k.weight"); k = oracle.matmul(xb, w, ty.id, dim, nkv * hd, 2)
+    ty, w = shard("l.0.attn.v.weight"); v = oracle.matmul(xb, w, ty.id, dim, nkv * hd, 2)
+    q = oracle.rope(q, hd, pos, cfg["rope_theta"], cfg["rotary_dim"])
+    k = oracle.rope(k, hd, pos, cfg["rope_theta"], cfg["rotary_dim"])
+    kb = np.zeros((4, nkv * hd), np.float16); vb = np.zeros((4, nkv * hd), np.float16)
+    kb[0], vb[0] = k.astype(np.float16), v.astype(np.float16)
+    att, _ = oracle.mha(q, kb.view(np.uint16), vb.view(np.uint16), hd, 1, 4, nh, nkv)
+    ty, w = shard("l.0.attn.down.weight"); part = oracle.matmul(att, w, ty.id, nh * hd, dim, 2)
+    red = torch.from_numpy(part.copy()); dist.all_reduce(red)                     # exchange 1
+    x = x + red.numpy()
+    ty, g = t["l.0.mlp.norm.weight"]
+    xb = oracle.rmsnorm(x, g, ty.id, cfg["norm_eps"])
+    ty, w = shard("l.0.mlp.gate.weight"); a = oracle.matmul(xb, w, ty.id, dim, hid, 2)
+    ty, w = shard("l.0.mlp.up.weight"); b = oracle.matmul(xb, w, ty.id, dim, hid, 2)
+    L = oracle.lib()
+    hb = np.array([L.orc_silu(float(z)) for z in a], np.float32) * b
+    ty, w = shard("l.0.mlp.down.weight"); part = oracle.matmul(hb, w, ty.id, hid, dim, 2)
+    red = torch.from_numpy(part.copy()); dist.all_reduce(red)                     # exchange 2
+    x = x + red.numpy()
+    if rank == 0:
+        out_q.put(x)
+
+
+def _worker(rank, size, port, wtype, out_q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    c = synth.model_config("tiny", n_layers=1)
+    cfg = X.parse_config(synth.metadata_strings(c))
+    tensors = [(n, t, np.ascontiguousarray(a).view(np.uint8).reshape(-1)) for n, t, a in synth.iter_tensors(c, T.parse(wtype), 0, std=0.06)]
+    x = synth.normal(3, 99, cfg["dim"], 1.0)
+    _layer_tp(rank, size, cfg, tensors, x, 5, out_q)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("wtype", ["f16", "q8_0", "q4_0"])
+def test_two_rank_layer_matches_unsharded_oracle(wtype):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 1000) + {"f16": 0, "q8_0": 1, "q4_0": 2}[wtype]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, wtype, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # unsharded: the oracle model itself, one layer, position 5 with an empty cache is not expressible through forward()
+    # (it would attend over 6 slots), so run the same ops with size 1 in-process via a 1-rank gloo group
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port + 7)
+    dist.init_process_group("gloo", rank=0, world_size=1)
+    try:
+        c = synth.model_config("tiny", n_layers=1)
+        cfg = X.parse_config(synth.metadata_strings(c))
+        tensors = [(n, t, np.ascontiguousarray(a).view(np.uint8).reshape(-1)) for n, t, a in synth.iter_tensors(c, T.parse(wtype), 0, std=0.06)]
+        x = synth.normal(3, 99, cfg["dim"], 1.0)
+        import queue
+        lq = queue.Queue()
+        _layer_tp(0, 1, cfg, tensors, x, 5, lq)
+        want = lq.get()
+    finally:
+        dist.destroy_process_group()
+    assert np.max(np.abs(got - want)) < 1e-5 * max(1.0, np.abs(want).max())
+
+
+def test_shard_plan_partitions_every_tensor():
+    c = synth.model_config("small")
+    cfg = X.parse_config(synth.metadata_strings(c))
+    for size in (1, 2):
+        for name, shape in X.expected_tensors(cfg).items():
+            if len(shape) == 1 or name == "embed.weight":
+                continue
+            cover = np.zeros(shape, np.int32)
+            for r in range(size):
+                (r0, r1), (c0, c1) = tp.shard_ranges(name, cfg, r, size)
+                cover[r0:r1, c0:c1] += 1
+                assert (c1 - c0) % 32 == 0 and c0 % 32 == 0            # no 32-element quantisation block is ever split
+            assert np.all(cover == 1), name
+    with pytest.raises(ValueError):
+        tp.shard_ranges("l.0.attn.q.weight", cfg, 0, 3)                  # 2 kv heads do not split 3 ways
