@@ -179,13 +179,14 @@ struct TmaArgs {
 	int U;          // units per stage
 	int NS;         // ring stages
 	int n_tiles;    // ceil(virtual rows / RC)
+	int x_global;   // 1: activations are NOT staged in shared memory but read through L1 (long rows without norm: W2), 8-row reuse
 };
 
 constexpr int TMA_NW = 8; // consumer warps
 
 __host__ __device__ inline size_t tma_smem_bytes(int type, int n, int RC, int U, int NS) {
 	size_t s = 0;
-	s += (size_t) n * sizeof(float);            // xb
+	s += (size_t) n * sizeof(float);            // xb (pass n = 0 when activations are read from global memory)
 	s += (size_t) NS * RC * U * unit_bytes(type); // ring
 	s += 2 * TMA_NW * 16 * sizeof(float);       // partials, double-buffered  [2][KW<=8][RC<=16]
 	s += 2 * (size_t) NS * sizeof(uint64_t);    // full / empty barriers
@@ -212,7 +213,8 @@ __global__ void __launch_bounds__((TMA_NW + 1) * 32, 1) matvec_tma_kernel(const 
 
 	extern __shared__ __align__(128) uint8_t smem[];
 	float* xb = reinterpret_cast<float*>(smem);
-	uint8_t* ring = smem + (((size_t) a.n * sizeof(float) + 127) / 128) * 128;
+	const bool xg = !NORM && ta.x_global;
+	uint8_t* ring = smem + (xg ? 0 : (((size_t) a.n * sizeof(float) + 127) / 128) * 128);
 	float* part = reinterpret_cast<float*>(ring + (size_t) NS * RC * row_stage_bytes);
 	uint64_t* full = reinterpret_cast<uint64_t*>(part + 2 * TMA_NW * 16);
 	uint64_t* empty = full + NS;
@@ -273,7 +275,7 @@ __global__ void __launch_bounds__((TMA_NW + 1) * 32, 1) matvec_tma_kernel(const 
 		}
 	}
 	// ---- stage activations: xb = NORM ? x * scale * g : x ----
-	{
+	if (!xg) {
 		// xb is stored permuted inside each 256-element unit: the E floats a lane needs for one piece are split into
 		// E/4 float4s laid out [i][piece], so the 32 lanes of a warp read consecutive float4s (no bank conflicts).
 		auto xpos = [](int e) { // e % 4 == 0
@@ -317,6 +319,12 @@ __global__ void __launch_bounds__((TMA_NW + 1) * 32, 1) matvec_tma_kernel(const 
 		f32x2 acc[R];
 #pragma unroll
 		for (int r = 0; r < R; r++) acc[r] = pack2(0.f, 0.f);
+		// residual: the reducer warp fetches the old activation now, so its epilogue does not sit on an L2 round trip
+		float xold = 0.f;
+		if (a.epi == EPI_RESIDUAL && warp == (tt % TMA_NW) && lane < RC) {
+			const int row = ((int) blockIdx.x + tt * (int) gridDim.x) * RC + lane;
+			if (row < a.d) xold = a.out[row];
+		}
 		for (int st = 0; st < stages_per_tile; st++) {
 			const int u0 = st * U;
 			const int un = min(U, nu - u0);
@@ -328,11 +336,20 @@ __global__ void __launch_bounds__((TMA_NW + 1) * 32, 1) matvec_tma_kernel(const 
 			for (int p = kw * per + lane; p < pend; p += 32) {
 				const int u = p / PPU, pp = p % PPU;
 				float xv[E];
-				const float* xs = xb + (size_t) (u0 + u) * 256 + pp * 4;
+				if (xg) { // natural order, straight from global memory through L1 (coherent at a kernel boundary)
+					const float* xs = a.x + (size_t) (u0 + u) * 256 + pp * E;
 #pragma unroll
-				for (int i = 0; i < E; i += 4) {
-					const float4 v = *reinterpret_cast<const float4*>(xs + i * PPU);
-					xv[i] = v.x; xv[i + 1] = v.y; xv[i + 2] = v.z; xv[i + 3] = v.w;
+					for (int i = 0; i < E; i += 4) {
+						const float4 v = ld_act4(xs + i);
+						xv[i] = v.x; xv[i + 1] = v.y; xv[i + 2] = v.z; xv[i + 3] = v.w;
+					}
+				} else {
+					const float* xs = xb + (size_t) (u0 + u) * 256 + pp * 4;
+#pragma unroll
+					for (int i = 0; i < E; i += 4) {
+						const float4 v = *reinterpret_cast<const float4*>(xs + i * PPU);
+						xv[i] = v.x; xv[i + 1] = v.y; xv[i + 2] = v.z; xv[i + 3] = v.w;
+					}
 				}
 #pragma unroll
 				for (int r = 0; r < R; r++) {
@@ -363,13 +380,11 @@ __global__ void __launch_bounds__((TMA_NW + 1) * 32, 1) matvec_tma_kernel(const 
 			// gather the RC sums into lane 0 .. (pairs stay adjacent for RoPE): each even lane takes its neighbour's value
 			const float ynext = __shfl_down_sync(0xffffffffu, yv, 1);
 			const int row0 = ((int) blockIdx.x + tt * (int) gridDim.x) * RC;
-			if (lane < RC && (lane & 1) == 0) {
+			if (a.epi == EPI_RESIDUAL) {
+				if (lane < RC && row0 + lane < a.d) a.out[row0 + lane] = xold + yv;
+			} else if (lane < RC && (lane & 1) == 0 && a.epi != EPI_GLU) { // GLU below (partner rows RC/2 apart)
 				const float y2[2] = {yv, ynext};
-				if (a.epi == EPI_GLU) {
-					// handled below (needs W1/W3 partner rows RC/2 apart)
-				} else {
-					epilogue<2>(a, row0 + lane, y2);
-				}
+				epilogue<2>(a, row0 + lane, y2);
 			}
 			if (a.epi == EPI_GLU) {
 				const float ypart = __shfl_down_sync(0xffffffffu, yv, RC / 2); // W3 value for the W1 row in this lane

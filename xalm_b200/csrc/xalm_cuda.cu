@@ -58,6 +58,7 @@ static std::map<std::string, int>& tuning() {
 	    {"tma", 1},          // stream weights with cp.async.bulk into a shared-memory ring (matvec_tma.cuh)
 	    {"tma_smem_kb", 100}, // shared-memory budget per CTA for the TMA kernel (two kernels co-reside under PDL)
 	    {"tma_rc_small", 8}, // rows per tile when the matrix has few rows (Wo, W2)
+	    {"tma_xstage_max_kb", 32}, // rows longer than this (in fp32 bytes) are not staged in smem when there is no norm
 	    {"tma_rc", 0},       // 0 = auto, else force rows per tile (4 or 8)
 	    {"tma_ns_max", 4},   // most ring stages
 	    {"tma_ctas_per_sm", 2},
@@ -216,7 +217,10 @@ static int launch_matvec_tma(const MatvecArgs& a, cudaStream_t s, bool pdl) {
 	if (vrows % RC) return -1;
 	const int ub = unit_bytes(t);
 	const size_t budget = (size_t) tune("tma_smem_kb") * 1024;
-	const size_t fixed = tma_smem_bytes(t, a.n, RC, 0, 0) + 2 * 4 * sizeof(uint64_t);
+	// long rows without a norm prologue (W2): do not spend shared memory on x, read it through L1 with 8-row reuse
+	const bool x_global = a.norm_w == nullptr && RC == 8 && (size_t) a.n * sizeof(float) > (size_t) tune("tma_xstage_max_kb") * 1024;
+	const int n_stage = x_global ? 0 : a.n;
+	const size_t fixed = tma_smem_bytes(t, n_stage, RC, 0, 0) + 2 * 4 * sizeof(uint64_t);
 	if (fixed + 2 * (size_t) RC * ub > 200 * 1024) return -1; // activations do not fit: LDG path
 	// stage: U units per row, chosen to keep >= 32 pieces per K-slice, as large as the budget allows with >= 2 stages
 	int umin = (32 * KW + ppu - 1) / ppu;
@@ -233,11 +237,12 @@ static int launch_matvec_tma(const MatvecArgs& a, cudaStream_t s, bool pdl) {
 		if ((size_t) ns * stage > best) { best = (size_t) ns * stage; U = u; NS = ns; }
 	}
 	if (best == 0) { U = umin; NS = 2; }
-	const size_t smem = tma_smem_bytes(t, a.n, RC, U, NS);
+	const size_t smem = tma_smem_bytes(t, n_stage, RC, U, NS);
 	if (smem > 200 * 1024) return -1;
 	TmaArgs ta;
 	ta.a = a;
 	ta.U = U; ta.NS = NS;
+	ta.x_global = x_global ? 1 : 0;
 	ta.n_tiles = (vrows + RC - 1) / RC;
 	const int grid = tune("tma_ctas_per_sm"); // upper bound on resident CTAs per SM; the launcher asks the occupancy API
 	const bool norm = a.norm_w != nullptr;
