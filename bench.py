@@ -142,7 +142,8 @@ def run_reference(args):
     cfg_full = synth.model_config(args.shape)
     cfg = X.parse_config(synth.metadata_strings(cfg_full), args.ctx)
     wtype = T.parse(args.wtype)
-    cores = os.cpu_count() or 1
+    cores = oracle.set_threads(os.cpu_count() or 1)      # torchrun exports OMP_NUM_THREADS=1: ask for every core
+    synth.set_threads(cores)
     t0 = time.time()
     tensors = {name: (t.id, np.ascontiguousarray(arr).view(np.uint8).reshape(-1)) for name, t, arr in synth.iter_tensors(cfg_full, wtype, args.seed)}
     gen_s = time.time() - t0
@@ -213,7 +214,8 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local_rank))
-        os.environ["OMP_NUM_THREADS"] = str(max(1, (os.cpu_count() or 8) // world))
+    from xalm_b200 import synth as _synth
+    _synth.set_threads(max(1, (os.cpu_count() or 8) // world))   # torchrun exports OMP_NUM_THREADS=1
 
     def barrier():
         if world > 1:
@@ -315,6 +317,7 @@ def main():
     # ---- CPU baseline beside it: the oracle port on the host cores, same weights (rank 0, N = 1 only) ----
     if keep_host:
         from oracle import oracle
+        cpu_cores = oracle.set_threads(os.cpu_count() or 1)
         om = oracle.OracleModel(cfg, host_tensors, acc_mode=1)
         tok = 1
         lg = om.forward(tok, 0, 1)          # warm-up (touches every page)
@@ -325,7 +328,7 @@ def main():
             lg = om.forward(tok, 1 + i, 1)
         cdt = time.perf_counter() - t0
         om.close()
-        line["cpu_baseline"] = {"value": n / cdt, "unit": "tok/s", "cores": os.cpu_count(), "kind": "port",
+        line["cpu_baseline"] = {"value": n / cdt, "unit": "tok/s", "cores": cpu_cores, "kind": "port",
                                 "sample": f"{n} greedy tokens at positions 1..{n} of the same model (full depth, same weights), wall clock"}
     if rank == 0:
         print(json.dumps(line), flush=True)

@@ -67,10 +67,18 @@ def lib():
     L.orc_sample_prob.restype = C.c_float
     L.orc_sample_prob.argtypes = [vp, C.c_int, C.c_int]
     L.orc_sample_argmax.argtypes = [vp, C.c_int]
+    L.orc_set_threads.argtypes = [C.c_int]
+    L.orc_set_threads.restype = None
+    L.orc_num_threads.restype = C.c_int
     L.orc_active_bytes.restype = C.c_longlong
     L.orc_active_bytes.argtypes = [vp, C.c_longlong]
     _LIB = L
     return L
+
+
+def set_threads(n: int) -> int:
+    lib().orc_set_threads(int(n))
+    return int(lib().orc_num_threads())
 
 
 def _p(a: np.ndarray):

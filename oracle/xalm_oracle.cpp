@@ -522,6 +522,15 @@ long long orc_active_bytes(orc_model* m, long long pos) {
 	return bytes;
 }
 
+// torchrun exports OMP_NUM_THREADS=1 into every rank; the CPU-baseline leg asks for all cores explicitly
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+	if (n > 0) omp_set_num_threads(n);
+#else
+	(void) n;
+#endif
+}
+
 int orc_num_threads() {
 #ifdef _OPENMP
 	return omp_get_max_threads();

@@ -149,3 +149,15 @@ def test_sampler_quirk_on_device_logits():
     st.logits()[3] = 0.25
     assert Sampler(cfg).sample_argmax(st) == 3
     assert abs(Sampler(cfg).sample_prob(3, st) - oracle.sample_prob(st.logits(), 3)) < 1e-6
+
+
+@pytest.mark.parametrize("shape,wtype,layers", [("l70", "q8_0", 1), ("l8", "q4_0", 2)])
+def test_baseline_shapes_depth_reduced(shape, wtype, layers):
+    """BASELINE configs 4/5 at reduced depth (SURVEY.md §7 '70B parity'): Llama-70B dims (8192/28672, 64 q heads on 8 kv heads,
+    128k vocab) and Llama-8B dims, full width — exercises GQA 8:1, 28672-long rows (activations read through L1), big vocab."""
+    config, om, gm = synth_pair(shape, wtype, seed=3, std=0.02, n_layers=layers)
+    prompt = [int(t) for t in np.random.default_rng(1).integers(3, config["vocab_size"], size=6)]
+    otoks, gtoks, maxdiff, margin = greedy_compare(config, om, gm, prompt, 4)
+    assert maxdiff <= LOGIT_TOL, f"{shape}: logits differ by {maxdiff}"
+    assert otoks == gtoks, f"{shape}: greedy tokens diverge (min margin {margin})"
+    gm.close(); om.close()

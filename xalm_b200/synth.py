@@ -47,8 +47,14 @@ def host():
         L.xalm_host_quantize.argtypes = [C.c_int, C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p]
         L.xalm_host_normal.argtypes = [C.c_uint64, C.c_uint64, C.c_longlong, C.c_float, C.c_float, C.c_void_p]
         L.xalm_host_normal.restype = None
+        L.xalm_host_set_threads.argtypes = [C.c_int]
+        L.xalm_host_set_threads.restype = None
         _HOST = L
     return _HOST
+
+
+def set_threads(n: int):
+    host().xalm_host_set_threads(int(n))
 
 
 def normal(seed: int, stream: int, n: int, std: float, mean: float = 0.0) -> np.ndarray:
