@@ -120,6 +120,12 @@ def build_model_streaming(cfg_full: dict, cfg: dict, wtype, seed: int, keep_host
     if model.tp_size > 1:
         buf = (C.c_char * 128).from_buffer_copy(cuda_kw["comm_id"])
         capi.check(L.xalm_cuda_comm_init(h, buf))
+        if cuda_kw.get("ipc_exchange") is not None:
+            mine = (C.c_char * 64)()
+            capi.check(L.xalm_cuda_ipc_export(h, mine))
+            table = cuda_kw["ipc_exchange"](bytes(mine))
+            tb = (C.c_char * len(table)).from_buffer_copy(table)
+            capi.check(L.xalm_cuda_ipc_import(h, tb))
     from xalm_b200 import xalm_file as X
     shapes = X.expected_tensors(cfg)
     host = {}
@@ -239,8 +245,12 @@ def main():
     stream = tstream.cuda_stream
     keep_host = (world == 1 and rank == 0 and not args.no_cpu_baseline)
     t0 = time.time()
+    ipc_exchange = None
+    if world > 1 and os.environ.get("XALM_TP_PEER", "1") != "0":
+        from xalm_b200 import tp as _tp
+        ipc_exchange = _tp.make_ipc_exchange(dist, world)
     model, host_tensors = build_model_streaming(cfg_full, cfg, wtype, args.seed, keep_host, device=local_rank, tp_rank=rank,
-                                                tp_size=world, comm_id=comm_id, stream=stream)
+                                                tp_size=world, comm_id=comm_id, stream=stream, ipc_exchange=ipc_exchange)
     gen_s = time.time() - t0
     ctx = cfg["max_seq_len"]
     pos_list = positions_for(args.steps, ctx)

@@ -97,6 +97,13 @@ void xalm_cuda_destroy(xalm_cuda_model* m);
 int xalm_cuda_comm_unique_id(void* id128);
 int xalm_cuda_comm_init(xalm_cuda_model* m, const void* id128);
 
+/* Optional: one-shot allreduce over NVLink peer memory instead of NCCL for the two per-layer exchanges.  Every rank exports
+ * a CUDA IPC handle of its exchange buffer, the host gathers all of them (rank order) and hands the table to every rank.
+ * Call after create and before finalize; without it the backend uses ncclAllReduce. */
+#define XALM_IPC_HANDLE_BYTES 64
+int xalm_cuda_ipc_export(xalm_cuda_model* m, void* handle64);
+int xalm_cuda_ipc_import(xalm_cuda_model* m, const void* handles /* tp_size x 64 bytes */);
+
 /* Run on a caller-provided cudaStream_t (e.g. the framework's current stream) instead of the model's own. */
 int xalm_cuda_set_stream(xalm_cuda_model* m, void* cuda_stream);
 

@@ -25,7 +25,9 @@ def main():
     cfg = X.parse_config(synth.metadata_strings(c))
     tensors = list(synth.iter_tensors(c, T.parse(wtype), seed=1, std=0.03))
     comm_id = tp.broadcast_comm_id(dist, rank, device="cuda")
-    gm = Model.from_tensors(cfg, tensors).cuda(device=local, tp_rank=rank, tp_size=world, comm_id=comm_id)
+    use_peer = os.environ.get("XALM_TP_PEER", "1") != "0"
+    gm = Model.from_tensors(cfg, tensors).cuda(device=local, tp_rank=rank, tp_size=world, comm_id=comm_id,
+                                               ipc_exchange=tp.make_ipc_exchange(dist, world) if use_peer else None)
     state, sampler = InferenceState(cfg).cuda(), Sampler(cfg)
     prompt = [int(t) for t in np.random.default_rng(0).integers(3, cfg["vocab_size"], size=40)]
     om = None

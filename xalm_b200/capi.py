@@ -50,6 +50,8 @@ SYMBOLS = {
     "xalm_cuda_destroy": (None, [_vp]),
     "xalm_cuda_comm_unique_id": (_i, [_vp]),
     "xalm_cuda_comm_init": (_i, [_vp, _vp]),
+    "xalm_cuda_ipc_export": (_i, [_vp, _vp]),
+    "xalm_cuda_ipc_import": (_i, [_vp, _vp]),
     "xalm_cuda_set_stream": (_i, [_vp, _vp]),
     "xalm_cuda_forward": (_i, [_vp, _i, _i, _i, _vp]),
     "xalm_cuda_forward_async": (_i, [_vp, _i, _i, _i]),

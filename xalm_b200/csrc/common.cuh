@@ -36,7 +36,8 @@ struct StepParams {
 	int kv_pos;  // infer.cpp:612
 	int kv_len;  // infer.cpp:613
 	int mode;
-	int pad[2];
+	unsigned int ar_base; // peer allreduce sequence base of this token (same on every rank)
+	int pad;
 };
 
 // ---- loads ---------------------------------------------------------------------------------------------

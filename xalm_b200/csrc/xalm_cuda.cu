@@ -345,6 +345,50 @@ __global__ void residual_add_kernel(float* __restrict__ x, const float* __restri
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) x[i] += y[i];
 }
 
+// ---- one-shot allreduce + residual over NVLink peer memory (tensor parallel) -------------------------------------------
+// Every rank's matvec wrote its partial vector into ITS OWN exchange buffer (slot = call index & 1).  This kernel
+//   1. publishes "my partial #seq is ready" into every peer's flag array (system-scope release after the kernel boundary),
+//   2. waits until all peers have published #seq in MY flag array (local polling),
+//   3. reads the P partials straight from peer memory (volatile loads: peer lines must not be served from a stale L1),
+//      sums them in rank order — identical bits on every rank — and adds the result to the residual stream x.
+// Two slots suffice: a rank can only reach call k+2 after every peer has signalled k+1, i.e. finished reading k.
+struct PeerArgs {
+	float* data[8];          // exchange buffers of all ranks (peer-mapped), [2][stride] floats each
+	unsigned int* flags[8];  // flag arrays of all ranks, [2][8] u32 each
+	int rank, size, stride;
+};
+__global__ void peer_allreduce_residual_kernel(const PeerArgs pa, float* __restrict__ x, int n, int idx, const StepParams* step) {
+	pdl_launch_dependents();
+	pdl_wait();
+	const int slot = idx & 1;
+	const unsigned int seq = step->ar_base + (unsigned int) idx + 1u;
+	if (blockIdx.x == 0 && threadIdx.x < pa.size) {
+		__threadfence_system();
+		unsigned int* f = pa.flags[threadIdx.x] + slot * 8 + pa.rank;
+		asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(seq) : "memory");
+	}
+	if (threadIdx.x < pa.size) {
+		const unsigned int* f = pa.flags[pa.rank] + slot * 8 + threadIdx.x;
+		unsigned int v;
+		do {
+			asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+		} while ((int) (v - seq) < 0);
+	}
+	__syncthreads();
+	for (int i = (blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += gridDim.x * blockDim.x * 4) {
+		float4 acc = *reinterpret_cast<const float4*>(x + i);
+		float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+		for (int p = 0; p < pa.size; p++) {
+			const float* src = pa.data[p] + (size_t) slot * pa.stride + i;
+			float4 v;
+			asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(src));
+			sum.x += v.x; sum.y += v.y; sum.z += v.z; sum.w += v.w;
+		}
+		acc.x += sum.x; acc.y += sum.y; acc.z += sum.z; acc.w += sum.w;
+		*reinterpret_cast<float4*>(x + i) = acc;
+	}
+}
+
 // standalone rmsnorm / rope for the op-level entry points (the hot path fuses both into the matvec kernel)
 __global__ void rmsnorm_kernel(float* o, const float* x, const uint8_t* w, int wtype, int size, float eps) {
 	__shared__ float s_red[32];
@@ -607,6 +651,12 @@ struct xalm_cuda_model {
 	int launches_per_token[2] = {0, 0};
 	int last_launches = 0;
 	ncclComm_t comm = nullptr;
+	// peer-memory allreduce
+	float* xchg = nullptr;            // [2][dim] floats + [2][8] u32 flags, cudaMalloc'd (IPC-exportable)
+	bool peer_ready = false;
+	xalm::PeerArgs peer = {};
+	std::vector<void*> peer_opened;
+	unsigned int token_serial = 0;
 	// megakernel (megakernel.cuh)
 	bool mega = false;
 	MkPhase* d_phases = nullptr;
@@ -711,6 +761,8 @@ void xalm_cuda_destroy(xalm_cuda_model* m) {
 	if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
 	for (int i = 0; i < 64; i++)
 		if (m->h_step_ev_used[i]) cudaEventDestroy(m->h_step_ev[i]);
+	for (void* p : m->peer_opened) cudaIpcCloseMemHandle(p);
+	if (m->xchg) cudaFree(m->xchg);
 	m->da.free_all();
 	if (m->staging.p) cudaFree(m->staging.p);
 	if (m->staging.flag) cudaFree(m->staging.flag);
@@ -723,6 +775,49 @@ void xalm_cuda_destroy(xalm_cuda_model* m) {
 int xalm_cuda_set_stream(xalm_cuda_model* m, void* cuda_stream) {
 	if (!m) return set_error(XALM_ERR_INVALID, "model is NULL");
 	m->stream = cuda_stream ? (cudaStream_t) cuda_stream : m->own_stream;
+	return XALM_OK;
+}
+
+int xalm_cuda_ipc_export(xalm_cuda_model* m, void* handle64) {
+	if (!m || !handle64) return set_error(XALM_ERR_INVALID, "model/handle is NULL");
+	if (m->finalized) return set_error(XALM_ERR_STATE, "ipc_export must precede finalize");
+	XALM_CUDA_CHECK(cudaSetDevice(m->device));
+	static_assert(sizeof(cudaIpcMemHandle_t) == XALM_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
+	if (!m->xchg) {
+		const size_t bytes = (size_t) 2 * m->c.dim * sizeof(float) + 2 * 8 * sizeof(unsigned int);
+		XALM_CUDA_CHECK(cudaMalloc((void**) &m->xchg, bytes)); // its own allocation: the IPC handle covers exactly this buffer
+		XALM_CUDA_CHECK(cudaMemset(m->xchg, 0, bytes));
+		XALM_CUDA_CHECK(cudaDeviceSynchronize());
+	}
+	cudaIpcMemHandle_t h;
+	XALM_CUDA_CHECK(cudaIpcGetMemHandle(&h, m->xchg));
+	memcpy(handle64, &h, sizeof h);
+	return XALM_OK;
+}
+
+int xalm_cuda_ipc_import(xalm_cuda_model* m, const void* handles) {
+	if (!m || !handles) return set_error(XALM_ERR_INVALID, "model/handles is NULL");
+	if (m->finalized) return set_error(XALM_ERR_STATE, "ipc_import must precede finalize");
+	if (!m->xchg) return set_error(XALM_ERR_STATE, "ipc_import before ipc_export");
+	if (m->tp_size > 8) return set_error(XALM_ERR_UNSUPPORTED, "peer allreduce supports up to 8 ranks");
+	XALM_CUDA_CHECK(cudaSetDevice(m->device));
+	const size_t data_floats = (size_t) 2 * m->c.dim;
+	for (int p = 0; p < m->tp_size; p++) {
+		float* base = nullptr;
+		if (p == m->tp_rank) base = m->xchg;
+		else {
+			cudaIpcMemHandle_t h;
+			memcpy(&h, (const char*) handles + (size_t) p * XALM_IPC_HANDLE_BYTES, sizeof h);
+			void* ptr = nullptr;
+			XALM_CUDA_CHECK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+			m->peer_opened.push_back(ptr);
+			base = (float*) ptr;
+		}
+		m->peer.data[p] = base;
+		m->peer.flags[p] = reinterpret_cast<unsigned int*>(base + data_floats);
+	}
+	m->peer.rank = m->tp_rank; m->peer.size = m->tp_size; m->peer.stride = m->c.dim;
+	m->peer_ready = true;
 	return XALM_OK;
 }
 
@@ -1008,9 +1103,14 @@ static int enqueue_token(xalm_cuda_model* m, int mode, cudaStream_t s, int* n_la
 		}
 		{ // Wo + residual
 			MatvecArgs a = a_wo;
+			if (tp && m->peer_ready) a.out = m->xchg + (size_t) ((2 * l) & 1) * c.dim;
 			XALM_TRY(launch_matvec(a, s, pdl));
 			nl++;
-			if (tp) {
+			if (tp && m->peer_ready) {
+				e = launch(peer_allreduce_residual_kernel, dim3(4), dim3(256), s, pdl, m->peer, m->x, c.dim, 2 * l, (const StepParams*) m->d_step);
+				if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "peer allreduce launch failed: %s", cudaGetErrorString(e));
+				nl++;
+			} else if (tp) {
 				XALM_NCCL_CHECK(g_nccl.AllReduce(m->part, m->part, c.dim, ncclFloat32, ncclSum, m->comm, s));
 				e = launch(residual_add_kernel, dim3(8), dim3(256), s, false, m->x, (const float*) m->part, c.dim);
 				if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "residual launch failed: %s", cudaGetErrorString(e));
@@ -1018,14 +1118,19 @@ static int enqueue_token(xalm_cuda_model* m, int mode, cudaStream_t s, int* n_la
 			}
 		}
 		{ // ffn pre-norm + W1,W3 + act*gate
-			XALM_TRY(launch_matvec(a_w13, s, pdl && !tp));
+			XALM_TRY(launch_matvec(a_w13, s, pdl && (!tp || m->peer_ready)));
 			nl++;
 		}
 		{ // W2 + residual
 			MatvecArgs a = a_w2;
+			if (tp && m->peer_ready) a.out = m->xchg + (size_t) ((2 * l + 1) & 1) * c.dim;
 			XALM_TRY(launch_matvec(a, s, pdl));
 			nl++;
-			if (tp) {
+			if (tp && m->peer_ready) {
+				e = launch(peer_allreduce_residual_kernel, dim3(4), dim3(256), s, pdl, m->peer, m->x, c.dim, 2 * l + 1, (const StepParams*) m->d_step);
+				if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "peer allreduce launch failed: %s", cudaGetErrorString(e));
+				nl++;
+			} else if (tp) {
 				XALM_NCCL_CHECK(g_nccl.AllReduce(m->part, m->part, c.dim, ncclFloat32, ncclSum, m->comm, s));
 				e = launch(residual_add_kernel, dim3(8), dim3(256), s, false, m->x, (const float*) m->part, c.dim);
 				if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "residual launch failed: %s", cudaGetErrorString(e));
@@ -1179,6 +1284,8 @@ int xalm_cuda_forward_async(xalm_cuda_model* m, int token, int pos, int mode) {
 	sp.kv_pos = sp.kv_sink + (pos - sp.kv_sink) % (c.max_seq_len - sp.kv_sink);
 	sp.kv_len = pos >= c.max_seq_len ? c.max_seq_len : pos + 1;
 	sp.mode = mode;
+	sp.ar_base = m->token_serial * 1024u; // 2 x n_layers <= 1024 exchanges per token; wraps consistently on every rank
+	m->token_serial++;
 	XALM_CUDA_CHECK(cudaMemcpyAsync(m->d_step, &sp, sizeof sp, cudaMemcpyHostToDevice, s));
 	XALM_CUDA_CHECK(cudaEventRecord(m->h_step_ev[slot], s));
 	if (tune("graph")) {

@@ -88,7 +88,7 @@ class Model:
 
     # ---- model.cuda() -----------------------------------------------------------------------------------------
     def cuda(self, device: int = 0, tp_rank: int = 0, tp_size: int = 1, comm_id: bytes | None = None, stream: int | None = None,
-             release_host: bool = False) -> "Model":
+             release_host: bool = False, ipc_exchange=None) -> "Model":
         L = capi.lib()
         h = C.c_void_p()
         cfg = capi.XalmConfig.from_dict(self.config)
@@ -103,6 +103,15 @@ class Model:
                     raise ValueError("tensor parallel needs the 128-byte communicator id from comm_unique_id()")
                 buf = (C.c_char * 128).from_buffer_copy(comm_id)
                 capi.check(L.xalm_cuda_comm_init(h, buf))
+                if ipc_exchange is not None:
+                    # peer-memory allreduce: export my buffer, let the host gather everyone's handle, import the table
+                    mine = (C.c_char * 64)()
+                    capi.check(L.xalm_cuda_ipc_export(h, mine))
+                    table = ipc_exchange(bytes(mine))
+                    if len(table) != 64 * tp_size:
+                        raise ValueError("ipc_exchange must return tp_size x 64 bytes")
+                    tb = (C.c_char * len(table)).from_buffer_copy(table)
+                    capi.check(L.xalm_cuda_ipc_import(h, tb))
             for name in list(self.tensors.keys()):
                 t, shape, raw = self.tensors[name]
                 self.upload(name, t, shape, raw)

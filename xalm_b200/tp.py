@@ -61,3 +61,16 @@ def broadcast_comm_id(dist, rank: int, device=None) -> bytes:
         buf = torch.frombuffer(bytearray(Model.comm_unique_id()), dtype=torch.uint8).to(buf.device)
     dist.broadcast(buf, 0)
     return bytes(buf.cpu().numpy().tobytes())
+
+
+def make_ipc_exchange(dist, world: int, device="cuda"):
+    """Returns the callable Model.cuda(ipc_exchange=...) wants: all-gather one 64-byte CUDA IPC handle per rank."""
+    import torch
+
+    def exchange(mine: bytes) -> bytes:
+        t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(device)
+        out = [torch.zeros(64, dtype=torch.uint8, device=device) for _ in range(world)]
+        dist.all_gather(out, t)
+        return b"".join(bytes(o.cpu().numpy().tobytes()) for o in out)
+
+    return exchange
