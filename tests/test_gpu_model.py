@@ -161,3 +161,19 @@ def test_baseline_shapes_depth_reduced(shape, wtype, layers):
     assert maxdiff <= LOGIT_TOL, f"{shape}: logits differ by {maxdiff}"
     assert otoks == gtoks, f"{shape}: greedy tokens diverge (min margin {margin})"
     gm.close(); om.close()
+
+
+def test_full_size_mistral_7b_q8_0_parity():
+    """BASELINE config 2 at FULL size (32 layers, 7.2 B weights, q8_0): the CPU oracle manages ~8 tok/s on the GPU box's
+    cores, so direct parity is affordable: 4 prompt tokens + 12 greedy steps, token-exact, logits within 1e-2, and the
+    ring/sink path exercised right after (-T is not needed: positions stay < 4096)."""
+    config, om, gm = synth_pair("m7", "q8_0", seed=0, std=0.02)
+    assert config["max_seq_len"] == 4096 and config["n_layers"] == 32
+    otoks, gtoks, maxdiff, margin = greedy_compare(config, om, gm, [1, 415, 28747, 1824], 12)
+    assert maxdiff <= LOGIT_TOL, f"logits differ by {maxdiff}"
+    assert otoks == gtoks, f"greedy tokens diverge (min margin {margin})"
+    # algorithmic bytes: Model::active_bytes == SURVEY.md §8d formula (7.555 GB + 0.131 MB per cached position)
+    from xalm_b200.model import active_bytes_formula
+    assert gm.active_bytes(0) == active_bytes_formula(config, 34 / 32, 0) == om.active_bytes(0)
+    assert abs(gm.active_bytes(0) / 1e9 - 7.555) < 0.01
+    gm.close(); om.close()

@@ -59,6 +59,7 @@ static std::map<std::string, int>& tuning() {
 	    {"tma_smem_kb", 100}, // shared-memory budget per CTA for the TMA kernel (two kernels co-reside under PDL)
 	    {"tma_rc_small", 8}, // rows per tile when the matrix has few rows (Wo, W2)
 	    {"tma_xstage_max_kb", 32}, // rows longer than this (in fp32 bytes) are not staged in smem when there is no norm
+	    {"tma_norm_kw4", 0}, {"tma_norm_smem_kb", 72},
 	    {"tma_rc", 0},       // 0 = auto, else force rows per tile (4 or 8)
 	    {"tma_ns_max", 4},   // most ring stages
 	    {"tma_ctas_per_sm", 2},
@@ -210,13 +211,18 @@ static int launch_matvec_tma(const MatvecArgs& a, cudaStream_t s, bool pdl) {
 	if (RC == 8 && KW == 8 && nu * ppu / 8 < 32) KW = 4;     // short rows: keep 32 lanes busy
 	if (tune("tma_rc") == 4 && ppu >= 16) { RC = 4; KW = 8; }
 	if (tune("tma_rc") == 8 && ppu >= 16) { RC = 8; KW = 8; }
+	// norm-fused kernels (QKV, W1|W3, classifier; n = dim): 4 K-slices x 2 row groups use fewer registers (<= 72), so three
+	// CTAs fit per SM with 17 KB stages — measured faster than 2 x (8 K-slices) for these, slower for Wo/W2 (profiles/)
+	bool norm_cfg = false;
+	if (a.norm_w != nullptr && ppu >= 16 && tune("tma_norm_kw4") && nu * ppu / 4 >= 32) { RC = 8; KW = 4; norm_cfg = true; }
 	const int force = tune("mv_cfg_rows");
+	if (force) norm_cfg = false;
 	if (force == 88) { RC = 8; KW = 8; }
 	if (force == 84) { RC = 8; KW = 4; }
 	if (force == 48) { RC = 4; KW = 8; }
 	if (vrows % RC) return -1;
 	const int ub = unit_bytes(t);
-	const size_t budget = (size_t) tune("tma_smem_kb") * 1024;
+	const size_t budget = (size_t) (norm_cfg ? tune("tma_norm_smem_kb") : tune("tma_smem_kb")) * 1024;
 	// long rows without a norm prologue (W2): do not spend shared memory on x, read it through L1 with 8-row reuse
 	const bool x_global = a.norm_w == nullptr && RC == 8 && (size_t) a.n * sizeof(float) > (size_t) tune("tma_xstage_max_kb") * 1024;
 	const int n_stage = x_global ? 0 : a.n;
@@ -244,7 +250,7 @@ static int launch_matvec_tma(const MatvecArgs& a, cudaStream_t s, bool pdl) {
 	ta.U = U; ta.NS = NS;
 	ta.x_global = x_global ? 1 : 0;
 	ta.n_tiles = (vrows + RC - 1) / RC;
-	const int grid = tune("tma_ctas_per_sm"); // upper bound on resident CTAs per SM; the launcher asks the occupancy API
+	const int grid = norm_cfg ? 3 : tune("tma_ctas_per_sm"); // upper bound on resident CTAs per SM; the launcher asks the occupancy API
 	const bool norm = a.norm_w != nullptr;
 	cudaError_t e;
 	switch (t) {
