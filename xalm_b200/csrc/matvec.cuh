@@ -50,6 +50,9 @@ struct MatvecArgs {
 	float qkv_clip;
 	// one-byte LUT formats
 	int lut_type;        // 0 = none, else the type id whose 256 values fill the shared-memory table
+	// L2 prefetcher hand-shake (prefetch.cuh): block 0 publishes "kernel #prog_idx of this token has started"
+	unsigned int* progress;
+	int prog_idx;
 };
 
 __device__ __forceinline__ float act_gelu(float x) { return 0.5f * x * (1.0f + tanhf(0.797885f * (x + 0.044715f * x * x * x))); }
@@ -155,7 +158,10 @@ __global__ void __launch_bounds__(NW * 32) matvec_kernel(const MatvecArgs a) {
 
 	pdl_launch_dependents();
 	int tl = -1;
-	if (blockIdx.x == 0 && threadIdx.x == 0) tl = tl_begin(200 + a.epi);
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		tl = tl_begin(200 + a.epi);
+		if (a.progress) *reinterpret_cast<volatile unsigned int*>(a.progress) = (unsigned int) a.prog_idx;
+	}
 
 	RowPtr rp[R];
 #pragma unroll
@@ -293,6 +299,7 @@ __global__ void __launch_bounds__(NW * 32) matvec_tq1_kernel(const MatvecArgs a)
 	const int row0 = (blockIdx.x * NW + warp) * R;
 	const bool active = row0 < vrows;
 	pdl_launch_dependents();
+	if (blockIdx.x == 0 && threadIdx.x == 0 && a.progress) *reinterpret_cast<volatile unsigned int*>(a.progress) = (unsigned int) a.prog_idx;
 	pdl_wait();
 	if (a.epi == EPI_QKV && blockIdx.x == 0 && a.step->kv_sink > 0) rotate_sinks(a, a.step->kv_sink);
 	float scale = 1.0f;

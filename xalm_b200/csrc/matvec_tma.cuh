@@ -232,7 +232,10 @@ __global__ void __launch_bounds__((TMA_NW + 1) * 32, KW == 4 ? 3 : 1) matvec_tma
 	__syncthreads();
 	pdl_launch_dependents();
 	int tl = -1;
-	if (blockIdx.x == 0 && threadIdx.x == 0) tl = tl_begin(100 + a.epi);
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		tl = tl_begin(100 + a.epi);
+		if (a.progress) *reinterpret_cast<volatile unsigned int*>(a.progress) = (unsigned int) a.prog_idx;
+	}
 
 	const int my_tiles = ((int) blockIdx.x < ta.n_tiles) ? (ta.n_tiles - 1 - (int) blockIdx.x) / (int) gridDim.x + 1 : 0;
 

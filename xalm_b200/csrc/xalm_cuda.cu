@@ -27,6 +27,7 @@
 #include "matvec.cuh"
 #include "matvec_tma.cuh"
 #include "megakernel.cuh"
+#include "prefetch.cuh"
 
 namespace xalm {
 
@@ -52,6 +53,8 @@ static std::map<std::string, int>& tuning() {
 	    {"attn_splits", 0},  // 0 = auto (~1 CTA per SM, at most 32 splits per kv head)
 	    {"attn_min_split", 128},
 	    {"mv_cfg_rows", 0},  // 0 = auto, 1 = force config A (R4 KS1 NW4), 2 = force config B (R2 KS4 NW8)
+	    {"l2_prefetch", 0},  // EXPERIMENTAL, measured slower (profiles/r1_experiments.md): side-branch warp prefetching upcoming weights into L2
+	    {"l2_window_mb", 48},
 	    {"mega", 0},         // EXPERIMENTAL (not faster yet): run all layers of a token in one persistent kernel (megakernel.cuh) when the model allows
 	    {"mega_smem_kb", 200},
 	    {"mega_rc_small", 4},
@@ -663,6 +666,12 @@ struct xalm_cuda_model {
 	xalm::PeerArgs peer = {};
 	std::vector<void*> peer_opened;
 	unsigned int token_serial = 0;
+	// L2 prefetcher (prefetch.cuh)
+	PrefetchItem* d_pf_items = nullptr;
+	int n_pf_items = 0;
+	unsigned int* d_progress = nullptr;
+	cudaStream_t side_stream = nullptr;
+	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 	// megakernel (megakernel.cuh)
 	bool mega = false;
 	MkPhase* d_phases = nullptr;
@@ -767,6 +776,9 @@ void xalm_cuda_destroy(xalm_cuda_model* m) {
 	if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
 	for (int i = 0; i < 64; i++)
 		if (m->h_step_ev_used[i]) cudaEventDestroy(m->h_step_ev[i]);
+	if (m->side_stream) cudaStreamDestroy(m->side_stream);
+	if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+	if (m->ev_join) cudaEventDestroy(m->ev_join);
 	for (void* p : m->peer_opened) cudaIpcCloseMemHandle(p);
 	if (m->xchg) cudaFree(m->xchg);
 	m->da.free_all();
@@ -1082,7 +1094,20 @@ static int enqueue_token(xalm_cuda_model* m, int mode, cudaStream_t s, int* n_la
 	const bool pdl = tune("pdl") != 0;
 	const bool tp = m->tp_size > 1;
 	int nl = 0;
-	cudaError_t e = launch(embed_kernel, dim3(4), dim3(256), s, false, m->embed_type, (const uint8_t*) m->embed_raw, m->embed_row_bytes,
+	cudaError_t e;
+	const bool prefetch = m->d_pf_items != nullptr && tune("l2_prefetch") && !m->mega;
+	if (prefetch) { // fork: one warp on a side branch pulls upcoming weights into L2 (prefetch.cuh)
+		XALM_CUDA_CHECK(cudaMemsetAsync(m->d_progress, 0, sizeof(unsigned int), s));
+		XALM_CUDA_CHECK(cudaEventRecord(m->ev_fork, s));
+		XALM_CUDA_CHECK(cudaStreamWaitEvent(m->side_stream, m->ev_fork, 0));
+		const int n_items = mode == XALM_OUTPUT_LOGITS ? m->n_pf_items : m->n_pf_items - 1;
+		l2_prefetch_kernel<<<1, 32, 0, m->side_stream>>>(m->d_pf_items, n_items, m->d_progress, (unsigned long long) tune("l2_window_mb") << 20,
+		                                                  50ull * 1000 * 1000);
+		XALM_CUDA_CHECK(cudaGetLastError());
+		XALM_CUDA_CHECK(cudaEventRecord(m->ev_join, m->side_stream));
+		nl++;
+	}
+	e = launch(embed_kernel, dim3(4), dim3(256), s, false, m->embed_type, (const uint8_t*) m->embed_raw, m->embed_row_bytes,
 	                       c.dim, (const StepParams*) m->d_step, m->x);
 	if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "embed launch failed: %s", cudaGetErrorString(e));
 	nl++;
@@ -1148,6 +1173,7 @@ static int enqueue_token(xalm_cuda_model* m, int mode, cudaStream_t s, int* n_la
 		MatvecArgs a = {};
 		a.w = m->wcls.m; a.x = m->x; a.n = c.dim; a.d = m->vocab_l; a.epi = EPI_STORE;
 		a.norm_w = m->rms_final; a.norm_type = m->rms_final_type; a.norm_eps = c.norm_eps; a.out = m->logits;
+		a.progress = m->d_progress; a.prog_idx = 4 * c.n_layers;
 		XALM_TRY(launch_matvec(a, s, pdl && !tp));
 		nl++;
 		if (tp) {
@@ -1155,6 +1181,7 @@ static int enqueue_token(xalm_cuda_model* m, int mode, cudaStream_t s, int* n_la
 			nl++;
 		}
 	}
+	if (prefetch) XALM_CUDA_CHECK(cudaStreamWaitEvent(s, m->ev_join, 0)); // join the side branch
 	if (n_launches) *n_launches = nl;
 	return XALM_OK;
 }
@@ -1170,6 +1197,7 @@ static void fill_layer_args(xalm_cuda_model* m, int l, MatvecArgs* qkv, AttnArgs
 		a.norm_w = L.rms_att; a.norm_type = L.rms_att_type; a.norm_eps = c.norm_eps;
 		a.out = m->q; a.step = m->d_step; a.k_cache = L.k_cache; a.v_cache = L.v_cache; a.rope_freq = m->rope_freq;
 		a.q_dim = m->q_dim_l; a.kv_dim = m->kv_dim_l; a.head_dim = c.head_dim; a.qkv_clip = c.qkv_clip;
+		a.progress = m->d_progress; a.prog_idx = 4 * l;
 		*qkv = a;
 	}
 	{
@@ -1183,18 +1211,21 @@ static void fill_layer_args(xalm_cuda_model* m, int l, MatvecArgs* qkv, AttnArgs
 		MatvecArgs a = {};
 		a.w = L.wo.m; a.x = m->xb2; a.n = m->q_dim_l; a.d = c.dim;
 		a.epi = tp ? EPI_STORE : EPI_RESIDUAL; a.out = tp ? m->part : m->x;
+		a.progress = m->d_progress; a.prog_idx = 4 * l + 1;
 		*wo = a;
 	}
 	{ // ffn pre-norm + W1,W3 + act*gate
 		MatvecArgs a = {};
 		a.w = L.w13.m; a.x = m->x; a.n = c.dim; a.d = m->hidden_l; a.epi = EPI_GLU; a.glu_off = m->hidden_l; a.act = c.act;
 		a.norm_w = L.rms_ffn; a.norm_type = L.rms_ffn_type; a.norm_eps = c.norm_eps; a.out = m->hb;
+		a.progress = m->d_progress; a.prog_idx = 4 * l + 2;
 		*w13 = a;
 	}
 	{ // W2 + residual
 		MatvecArgs a = {};
 		a.w = L.w2.m; a.x = m->hb; a.n = m->hidden_l; a.d = c.dim;
 		a.epi = tp ? EPI_STORE : EPI_RESIDUAL; a.out = tp ? m->part : m->x;
+		a.progress = m->d_progress; a.prog_idx = 4 * l + 3;
 		*w2 = a;
 	}
 }
@@ -1247,6 +1278,26 @@ int xalm_cuda_finalize(xalm_cuda_model* m) {
 	XALM_TRY(m->da.alloc((void**) &m->d_step, sizeof(StepParams)));
 	XALM_CUDA_CHECK(cudaMallocHost((void**) &m->h_step, 64 * sizeof(StepParams)));
 	XALM_CUDA_CHECK(cudaMallocHost((void**) &m->h_logits, (size_t) c.vocab_size * sizeof(float)));
+	{ // L2 prefetcher: the token's weight matrices in execution order
+		std::vector<PrefetchItem> items;
+		unsigned long long cum = 0;
+		auto add = [&](const WMat& w) {
+			PrefetchItem it;
+			it.ptr = w.p0; it.bytes = (unsigned long long) w.s0 * w.rows; it.cum_start = cum;
+			cum += it.bytes;
+			items.push_back(it);
+		};
+		for (auto& L : m->layers) { add(L.wqkv.m); add(L.wo.m); add(L.w13.m); add(L.w2.m); }
+		add(m->wcls.m);
+		XALM_TRY(m->da.alloc((void**) &m->d_pf_items, items.size() * sizeof(PrefetchItem)));
+		XALM_CUDA_CHECK(cudaMemcpy(m->d_pf_items, items.data(), items.size() * sizeof(PrefetchItem), cudaMemcpyHostToDevice));
+		m->n_pf_items = (int) items.size();
+		XALM_TRY(m->da.alloc((void**) &m->d_progress, 64));
+		XALM_CUDA_CHECK(cudaMemset(m->d_progress, 0, 64));
+		XALM_CUDA_CHECK(cudaStreamCreateWithFlags(&m->side_stream, cudaStreamNonBlocking));
+		XALM_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+		XALM_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+	}
 	XALM_TRY(setup_megakernel(m));
 	XALM_CUDA_CHECK(cudaDeviceSynchronize());
 	m->finalized = true;
