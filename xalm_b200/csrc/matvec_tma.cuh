@@ -196,7 +196,7 @@ __host__ __device__ inline size_t tma_smem_bytes(int type, int n, int RC, int U,
 
 // TYPE: weight format; RC: rows per tile; KW: K-slices (RW = 8/KW row groups, R = RC/RW rows per warp); NORM: rmsnorm prologue
 template <int TYPE, int RC, int KW, bool NORM>
-__global__ void __launch_bounds__((TMA_NW + 1) * 32, KW == 4 ? 3 : 1) matvec_tma_kernel(const TmaArgs ta) {
+__global__ void __launch_bounds__((TMA_NW + 1) * 32, 1) matvec_tma_kernel(const TmaArgs ta) {
 	using F = Fmt<TYPE>;
 	using UF = UFmt<TYPE>;
 	constexpr int E = F::E;
