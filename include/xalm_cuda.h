@@ -114,6 +114,19 @@ int xalm_cuda_forward(xalm_cuda_model* m, int token, int pos, int mode, float* l
 /* Enqueue only (no host sync, logits stay on the device): the device-timed leg of bench.py. */
 int xalm_cuda_forward_async(xalm_cuda_model* m, int token, int pos, int mode);
 int xalm_cuda_sync(xalm_cuda_model* m);
+/* ---- batched prefill: the loops of main.cpp:94-100 (prompt hydrate) and :244-254 (perplexity), which call
+ *      Model::forward once per position, as ONE pass over the weights on the tcgen05 tensor-core path ---------- */
+/* Positions pos0 .. pos0+n-1 (pos0 + n <= max_seq_len: no ring wrap; past that use xalm_cuda_forward).  Fills the KV
+ * cache exactly as n forward calls would (fp16-operand rounding aside).  want_logits: 0 = none (HYDRATE_KV_CACHE for
+ * every position), 1 = logits of the last position -> logits_host[vocab], 2 = every position -> logits_host[n*vocab].
+ * targets/probs_host (n entries each, or NULL; needs want_logits 2): probs_host[i] = Sampler::sample_prob(targets[i])
+ * on the logits of position pos0+i (sampler.cpp:18-33) — what perplexity mode takes the log of (main.cpp:251).
+ * logits_host may be NULL.  Synchronous.  Tensor operands are fp16 (fp32 accumulate): logits agree with the
+ * token-at-a-time path within the north star's 1e-2. */
+int xalm_cuda_prefill(xalm_cuda_model* m, const int* tokens, int n, int pos0, int want_logits, float* logits_host,
+                      const int* targets, float* probs_host);
+/* Enqueue only (no read-back, no host sync) — bench.py's device-timed leg. */
+int xalm_cuda_prefill_async(xalm_cuda_model* m, const int* tokens, int n, int pos0, int want_logits);
 /* Pinned host buffer the logits are copied into by xalm_cuda_forward (alias it as InferenceState::_logits). */
 float* xalm_cuda_logits_host(xalm_cuda_model* m);
 /* Model::active_bytes(pos) (model.cpp:12-35), 64-bit, per-format bytes; this rank's shard only. */
@@ -135,6 +148,9 @@ int xalm_cuda_matmul(float* xout, const float* x, const void* w, int type_id, in
 /* mha_cuda — the prototype the reference declares and never defines (model.h:308-313). att may be NULL. */
 int xalm_cuda_mha(float* xout, float* att, const uint16_t* kb, const uint16_t* vb, const float* q, int head_dim,
                   int kv_len, int max_seq_len, int n_heads, int n_kv_heads);
+/* The batched form of matmul: out(T,N) = a(T,K) . W(N,K)^T on the tcgen05 path (dequantise to fp16 tiles, UMMA, fp32
+ * accumulate).  split: 1 = fp16 activations, 2 = hi+lo fp16 pair. */
+int xalm_cuda_gemm(float* out, const float* a, const void* w, int type_id, int T, int K, int N, int split);
 /* rmsnorm(o, x, weight, size, eps) (infer.cpp:224-251); weight F32 or BF16 only. */
 int xalm_cuda_rmsnorm(float* o, const float* x, const void* weight, int weight_type, int size, float eps);
 /* rope(vec, d, head_dim, pos, theta, rotary_dim) (infer.cpp:305-322), in place. */
@@ -143,7 +159,7 @@ int xalm_cuda_rope(float* vec, int d, int head_dim, int pos, float theta, int ro
 int xalm_cuda_ffn(float* xout, const float* x, const void* w1, const void* w2, const void* w3, int type_id,
                   int hidden_dim, int dim, int act);
 
-/* Integer tuning knobs by name ("pdl", "graph", "attn_splits", "attn_min_split", "mv_cfg_rows"); an XALM_<KEY>
+/* Integer tuning knobs by name ("pdl", "graph", "attn_splits", "attn_min_split", "mv_cfg_rows", "prefill_split"); an XALM_<KEY>
  * environment variable overrides the stored value.  Takes effect for graphs captured afterwards. */
 int xalm_cuda_tune(const char* key, int value);
 
@@ -158,6 +174,10 @@ int xalm_cuda_timeline(int n_records, unsigned long long* out, int* n_out);
  * 2 = the fused gate|up kernel (2d rows -> d outputs through act*gate); with_norm: fuse the rmsnorm prologue.  Returns
  * mean milliseconds per launch (CUDA events on the launch stream). */
 int xalm_cuda_bench_matvec(int type_id, int n, int d, int epi, int with_norm, int n_buffers, int iters, float* ms_per_launch);
+
+/* Times `iters` launches of the tcgen05 GEMM kernel alone on resident fp16 tiles (T x K activations, N x K weights);
+ * mean milliseconds per launch.  2*T*N*K flops per launch. */
+int xalm_cuda_bench_gemm(int T, int N, int K, int split, int iters, float* ms_per_launch);
 
 #ifdef __cplusplus
 }

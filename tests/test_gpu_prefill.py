@@ -1,0 +1,138 @@
+"""Batched prefill / perplexity on the tcgen05 path (BASELINE config 3) against the oracle and the token-at-a-time path.
+
+* the GEMM alone, every weight format: out = a . W^T with W bit-exactly dequantised (capi.dequant is pinned to the oracle
+  in test_gpu_formats.py) and both operands rounded to fp16 exactly as the kernel rounds them -> tight tolerance;
+* the whole forward: logits of every position vs the CPU oracle run token by token (north star: max-abs 1e-2),
+  KV cache contents, perplexity probabilities (Sampler::sample_prob), chunked prefill, prefill followed by decode.
+"""
+import numpy as np
+import pytest
+
+from oracle import oracle
+from xalm_b200 import capi, synth
+from xalm_b200 import types as T
+from xalm_b200.model import InferenceState, Sampler
+
+from gpu_util import LOGIT_TOL, random_raw, synth_pair
+
+pytestmark = pytest.mark.gpu
+
+ALL = ["f32", "f16", "bf16", "f8_e2m5", "f8_e3m4", "f8_e4m3", "f8_e5m2", "q8", "qi8", "q8_0", "q4_0", "q4_1", "q5_0", "q5_1", "tq1_0"]
+
+
+def _fp16(x):
+    return x.astype(np.float16).astype(np.float32)
+
+
+@pytest.mark.parametrize("wtype", ALL)
+@pytest.mark.parametrize("split", [1, 2])
+def test_gemm_every_format(wtype, split):
+    t = T.parse(wtype)
+    Tn, K, N = 150, 512, 320           # ragged: T not a multiple of 128, N not a multiple of 256; K = 2 units (TMA layout) for block formats
+    raw = random_raw(t, N, K, seed=11)
+    w = capi.dequant(t.id, raw, N * K).reshape(N, K)
+    a = synth.normal(5, 77, Tn * K, 1.0).reshape(Tn, K)
+    out = capi.gemm(a, raw, t.id, K, N, split)
+    wh = _fp16(w).astype(np.float64)
+    if split == 1:
+        ref = _fp16(a).astype(np.float64) @ wh.T
+    else:
+        hi = _fp16(a)
+        ref = (hi.astype(np.float64) + _fp16(a - hi).astype(np.float64)) @ wh.T
+    scale = float(np.abs(ref).max())
+    assert np.max(np.abs(out - ref)) <= 2e-5 * scale + 1e-6, f"{wtype}: {np.max(np.abs(out - ref))} vs scale {scale}"
+    if split == 2:   # the hi+lo pair keeps the activations to ~fp32: what is left is the fp16 rounding of the weights
+        exact = a.astype(np.float64) @ wh.T
+        assert np.max(np.abs(out - exact)) <= 2e-5 * scale + 1e-6
+
+
+@pytest.mark.parametrize("shape", [(1, 256, 256), (128, 64, 256), (129, 96, 32), (300, 2816, 1024)])
+def test_gemm_shapes(shape):
+    Tn, K, N = shape
+    t = T.parse("f16")
+    raw = random_raw(t, N, K, seed=3)
+    w = capi.dequant(t.id, raw, N * K).reshape(N, K)
+    a = synth.normal(6, 78, Tn * K, 1.0).reshape(Tn, K)
+    out = capi.gemm(a, raw, t.id, K, N, 1)
+    ref = _fp16(a).astype(np.float64) @ w.astype(np.float64).T
+    assert np.max(np.abs(out - ref)) <= 2e-5 * float(np.abs(ref).max()) + 1e-6
+
+
+def _oracle_all_logits(om, tokens):
+    return np.stack([om.forward(int(tok), pos, 1).copy() for pos, tok in enumerate(tokens)])
+
+
+@pytest.mark.parametrize("wtype,shape,n", [("f16", "tiny", 100), ("q8_0", "tiny", 128), ("q4_0", "tiny", 37), ("q5_1", "tiny", 70),
+                                           ("q8_0", "small", 200), ("f16", "small", 130)])
+@pytest.mark.parametrize("split", [1, 2])
+def test_prefill_logits_match_oracle(wtype, shape, n, split):
+    capi.tune("prefill_split", split)
+    try:
+        config, om, gm = synth_pair(shape, wtype, seed=7, std=0.06 if shape == "tiny" else 0.03)
+        rng = np.random.default_rng(1)
+        tokens = rng.integers(3, config["vocab_size"], size=n).astype(np.int32)
+        ref = _oracle_all_logits(om, tokens)
+        got = gm.prefill(tokens, 0, want_logits=2)
+        diff = float(np.max(np.abs(got - ref)))
+        assert diff <= LOGIT_TOL, f"{wtype}/{shape}: prefill logits differ from the oracle by {diff}"
+        assert np.array_equal(np.argmax(got, axis=1), np.argmax(ref, axis=1)) or diff < 1e-3
+        # the KV cache the prefill leaves behind is the one the token loop would have written (fp16-operand rounding aside)
+        for layer in range(config["n_layers"]):
+            for which in (0, 1):
+                kvd = config["n_kv_heads"] * config["head_dim"]
+                a = gm.read_kv(layer, which).view(np.float16).astype(np.float32)[: n * kvd]
+                b = om.kv(layer, which).view(np.float16).astype(np.float32)[: n * kvd]
+                assert np.max(np.abs(a - b)) <= 1e-2 * max(1.0, float(np.abs(b).max()))
+        gm.close(); om.close()
+    finally:
+        capi.tune("prefill_split", 1)
+
+
+def test_prefill_then_decode_and_last_logits():
+    """Prompt hydrate through prefill (want 1 = last position only), then the greedy loop on the decode kernels."""
+    config, om, gm = synth_pair("tiny", "q8_0", seed=9, std=0.06)
+    prompt = [1] + list(np.random.default_rng(2).integers(3, config["vocab_size"], size=60))
+    for pos, tok in enumerate(prompt):
+        lg_o = om.forward(int(tok), pos, 1 if pos + 1 == len(prompt) else 0)
+    lg = gm.prefill(np.array(prompt, dtype=np.int32), 0, want_logits=1)
+    assert np.max(np.abs(lg - lg_o)) <= LOGIT_TOL
+    state, sampler = InferenceState(config), Sampler(config)
+    state.logits()[:] = lg
+    otoks, gtoks = [], []
+    for i in range(16):
+        to, tg = oracle.sample_argmax(lg_o), sampler.sample_argmax(state)
+        otoks.append(to); gtoks.append(tg)
+        pos = len(prompt) + i
+        lg_o = om.forward(to, pos, 1)
+        gm.forward(state, tg, pos, 1)
+        assert np.max(np.abs(state.logits() - lg_o)) <= LOGIT_TOL
+    assert otoks == gtoks
+    gm.close(); om.close()
+
+
+def test_chunked_prefill_and_hydrate_mode():
+    config, om, gm = synth_pair("tiny", "f16", seed=10, std=0.06)
+    tokens = np.random.default_rng(3).integers(3, config["vocab_size"], size=120).astype(np.int32)
+    ref = _oracle_all_logits(om, tokens)
+    assert gm.prefill(tokens[:50], 0, want_logits=0) is None            # hydrate only
+    got = gm.prefill(tokens[50:], 50, want_logits=2)                   # second chunk attends to the first through the cache
+    assert np.max(np.abs(got - ref[50:])) <= LOGIT_TOL
+    with pytest.raises(capi.XalmError):                                 # would wrap the ring: not a prefill job
+        gm.prefill(tokens, config["max_seq_len"] - 10, want_logits=0)
+    gm.close(); om.close()
+
+
+def test_perplexity_probabilities():
+    """main.cpp:244-258: logprob = log(sample_prob(next token)) at every position."""
+    config, om, gm = synth_pair("tiny", "q8_0", seed=12, std=0.06)
+    tokens = np.random.default_rng(4).integers(3, config["vocab_size"], size=101).astype(np.int32)
+    ref_lp = []
+    for pos in range(100):
+        lg = om.forward(int(tokens[pos]), pos, 1)
+        ref_lp.append(np.log(oracle.sample_prob(lg, int(tokens[pos + 1]))))
+    _, probs = gm.prefill(tokens[:-1], 0, want_logits=2, targets=tokens[1:])
+    lp = np.log(probs)
+    assert np.max(np.abs(lp - np.array(ref_lp))) <= 2e-2
+    ppl_ref, ppl = np.exp(-np.mean(ref_lp)), np.exp(-np.mean(lp))
+    assert abs(ppl - ppl_ref) <= 2e-3 * ppl_ref
+    gm.close(); om.close()

@@ -39,16 +39,31 @@ def _sources(d, exts):
     return out
 
 
+CUDA_TUS = ["xalm_cuda.cu", "prefill.cu"]   # translation units of libxalm_cuda.so (objects cached under csrc/.obj)
+
+
 def build_cuda(force: bool = False, verbose: bool = False, extra=()) -> str:
-    deps = _sources(CSRC, (".cu", ".cuh")) + [os.path.join(ROOT, "include", "xalm_cuda.h")]
-    if not force and _newer(LIB, deps):
-        return LIB
-    cmd = [NVCC, *NVCC_FLAGS, *extra, "-shared", "-o", LIB, os.path.join(CSRC, "xalm_cuda.cu"), "-ldl"]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-        print(" ".join(cmd))
-    subprocess.check_call(cmd)
+    hdrs = _sources(CSRC, (".cuh", ".h")) + [os.path.join(ROOT, "include", "xalm_cuda.h")]
+    hdrs = [h for h in hdrs if os.sep + "host" + os.sep not in h]
+    objdir = os.path.join(CSRC, ".obj")
+    os.makedirs(objdir, exist_ok=True)
+    objs, procs = [], []
+    for tu in CUDA_TUS:
+        src = os.path.join(CSRC, tu)
+        obj = os.path.join(objdir, tu.replace(".cu", ".o"))
+        objs.append(obj)
+        if not force and not extra and _newer(obj, [src] + hdrs):
+            continue
+        cmd = [NVCC, *NVCC_FLAGS, *extra, "-c", "-o", obj, src]
+        if verbose:
+            cmd[1:1] = ["-Xptxas", "-v"]
+            print(" ".join(cmd))
+        procs.append((cmd, subprocess.Popen(cmd)))
+    for cmd, p in procs:
+        if p.wait() != 0:
+            raise subprocess.CalledProcessError(p.returncode, cmd)
+    if procs or not os.path.exists(LIB) or not _newer(LIB, objs):
+        subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs, "-ldl", "-ccbin", GXX])
     return LIB
 
 

@@ -70,6 +70,10 @@ SYMBOLS = {
     "xalm_cuda_tune": (_i, [C.c_char_p, _i]),
     "xalm_cuda_timeline": (_i, [_i, _vp, C.POINTER(_i)]),
     "xalm_cuda_bench_matvec": (_i, [_i, _i, _i, _i, _i, _i, _i, _fp]),
+    "xalm_cuda_prefill": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
+    "xalm_cuda_prefill_async": (_i, [_vp, _vp, _i, _i, _i]),
+    "xalm_cuda_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i]),
+    "xalm_cuda_bench_gemm": (_i, [_i, _i, _i, _i, _i, _fp]),
 }
 
 _LIB = None
@@ -176,4 +180,20 @@ def timeline_stop(n_records: int) -> np.ndarray:
 def bench_matvec(type_id: int, n: int, d: int, n_buffers: int, iters: int, epi: int = 0, with_norm: bool = False) -> float:
     ms = C.c_float(0)
     check(lib().xalm_cuda_bench_matvec(type_id, n, d, epi, int(with_norm), n_buffers, iters, C.byref(ms)))
+    return ms.value
+
+
+def gemm(a: np.ndarray, w_raw: np.ndarray, type_id: int, K: int, N: int, split: int = 1) -> np.ndarray:
+    """out(T,N) = a(T,K) . W(N,K)^T on the tensor-core path."""
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    T = a.shape[0]
+    w_raw = np.ascontiguousarray(w_raw)
+    out = np.empty((T, N), dtype=np.float32)
+    check(lib().xalm_cuda_gemm(_p(out), _p(a), _p(w_raw), type_id, T, K, N, split))
+    return out
+
+
+def bench_gemm(T: int, N: int, K: int, split: int = 1, iters: int = 20) -> float:
+    ms = C.c_float(0)
+    check(lib().xalm_cuda_bench_gemm(T, N, K, split, iters, C.byref(ms)))
     return ms.value

@@ -99,12 +99,13 @@ struct Timeline {
 	unsigned int cap;
 	unsigned int count;
 };
-__device__ Timeline d_timeline = {nullptr, 0, 0}; // single translation unit
 __device__ __forceinline__ unsigned long long gtime() {
 	unsigned long long t;
 	asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
 	return t;
 }
+#ifndef XALM_SECONDARY_TU // the timeline lives in xalm_cuda.cu's translation unit only
+__device__ Timeline d_timeline = {nullptr, 0, 0};
 __device__ __forceinline__ int tl_begin(int kid) {
 	if (d_timeline.buf == nullptr) return -1;
 	const unsigned int slot = atomicAdd(&d_timeline.count, 1u);
@@ -116,6 +117,10 @@ __device__ __forceinline__ int tl_begin(int kid) {
 __device__ __forceinline__ void tl_mark(int slot, int which) {
 	if (slot >= 0) d_timeline.buf[4 * slot + which] = gtime();
 }
+#else
+__device__ __forceinline__ int tl_begin(int) { return -1; }
+__device__ __forceinline__ void tl_mark(int, int) {}
+#endif
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

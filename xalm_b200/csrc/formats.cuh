@@ -163,6 +163,7 @@ __host__ inline PlaneSizes plane_row_bytes(int t, int n) {
 	}
 }
 
+#ifndef XALM_SECONDARY_TU // non-template kernels: defined once, in xalm_cuda.cu's translation unit
 // raw (on-disk rows, `raw_stride` bytes apart) -> planes.  One thread per block (or per 16 bytes for scalar types).
 __global__ void repack_kernel(int t, const uint8_t* __restrict__ raw, size_t raw_stride, int rows, int n, uint8_t* p0,
                               size_t s0, uint8_t* p1, size_t s1, uint8_t* p2, size_t s2) {
@@ -225,6 +226,7 @@ __global__ void fp8_scan_nonfinite_kernel(int t, const uint8_t* __restrict__ p, 
 	}
 	if (bad) *flag = 1;
 }
+#endif // XALM_SECONDARY_TU
 
 // ---------------------------------------------------------------------------------------------------------
 // Chunk arithmetic for the matvec kernel.  A "chunk" is what one lane fetches with ONE 16-byte load from the

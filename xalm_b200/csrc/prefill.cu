@@ -1,0 +1,1074 @@
+// prefill.cu — batched prefill / perplexity (BASELINE config 3): the whole prompt goes through every layer at once,
+// the seven per-layer contractions become GEMMs on the 5th-generation tensor cores (tcgen05.mma, accumulators in
+// TMEM), everything else stays the reference's arithmetic (infer.cpp:365-496) applied to T rows instead of one.
+//
+// What the reference does instead: main.cpp:244-254 (perplexity) and :94-100 (prompt hydrate) call Model::forward once
+// per position — T matvec passes over all weights.  Here the weights are read once per prompt.
+//
+// Data flow per layer (T = tokens in this call, all buffers in HBM, sized for Tp = ceil(T/128)*128 rows):
+//   x fp32 (T,dim) --rmsnorm_rows--> xb  [A tiles fp16]
+//   xb . Wqkv^T    --gemm, QKV epilogue (clip, RoPE at pos0+row, fp16)--> q (T,q_dim) fp16; K/V cache rows pos0..pos0+T-1
+//   causal attention over the fp16 cache (flash-style, mma.sync tiles, fp32 online softmax) --> xb2 [A tiles]
+//   xb2 . Wo^T     --gemm, residual epilogue--> x += .
+//   x --rmsnorm_rows--> xb;  xb . (W1|W3)^T --gemm, GLU epilogue act(g)*u--> hb [A tiles]
+//   hb . W2^T      --gemm, residual epilogue--> x += .
+// then final rmsnorm, classifier GEMM -> logits fp32 (rows, vocab), and softmax-at-target for perplexity.
+//
+// Operand layout ("A tiles"/"B tiles"): 128 (A) or 256 (B) rows x 64 K-elements of fp16, stored as the exact
+// shared-memory image tcgen05.mma wants for a K-major SWIZZLE_128B operand (8-row x 128-byte atoms, 16-byte chunks
+// XOR-swizzled by row%8), tile after tile.  One cp.async.bulk (TMA engine) brings a whole 16/32 KB tile into shared
+// memory — no tensor map, no per-thread staging.  Weights are dequantised from their decode layout into B tiles once
+// per GEMM (dequant_tiles_kernel: every format the decode path takes), which costs 2 bytes written + read per weight
+// against 2*T flops per weight: ~10 % of the GEMM at T = 4096.
+//
+// Numerics: tensor-core operands are fp16 with fp32 accumulation.  split=2 keeps the activations to ~fp32 by feeding
+// hi = fp16(a) and lo = fp16(a - hi) as two MMAs against the same weight tile.  Tolerance in tests: logits within 1e-2
+// of the token-at-a-time path (north star: "within max-abs 1e-2 (fp16)").
+#define XALM_SECONDARY_TU
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <float.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "matvec.cuh"
+#include "prefill.h"
+
+namespace xalm {
+
+// ------------------------------------------------------------------------------------------------------------------
+// tile geometry
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int GB_M = 128;  // rows of an A tile = UMMA M
+constexpr int GB_N = 256;  // rows of a B tile = UMMA N
+constexpr int GB_K = 64;   // K elements per tile = one 128-byte swizzle row of fp16
+constexpr int A_TILE_BYTES = GB_M * GB_K * 2;
+constexpr int B_TILE_BYTES = GB_N * GB_K * 2;
+constexpr int UMMA_K = 16;
+
+// byte offset of element (r, c) inside a tile (r < 128 or 256, c < 64): 8-row atoms of 1024 bytes, chunk ^= row % 8
+__host__ __device__ __forceinline__ size_t tile_inner_off(int r, int c) {
+	return (size_t) (r >> 3) * 1024 + (size_t) (r & 7) * 128 + (size_t) ((((c >> 3) ^ r) & 7) << 4) + (size_t) (c & 7) * 2;
+}
+__host__ __device__ __forceinline__ size_t a_off(int m, int k, int KT) {
+	return ((size_t) (m / GB_M) * KT + (size_t) (k / GB_K)) * A_TILE_BYTES + tile_inner_off(m % GB_M, k % GB_K);
+}
+
+struct ATiles {      // activations as tensor-core operands
+	uint8_t* hi = nullptr;
+	uint8_t* lo = nullptr; // residual plane (split = 2), else nullptr
+	int KT = 0;      // K tiles per row block
+};
+
+// pack 8 floats into 8 fp16 (hi) and, optionally, the fp16 of the rounding residuals (lo)
+__device__ __forceinline__ void store_a8(const ATiles& a, int m, int k0, const float (&v)[8]) {
+	const size_t off = a_off(m, k0, a.KT);
+	__half2 h[4];
+#pragma unroll
+	for (int i = 0; i < 4; i++) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+	*reinterpret_cast<uint4*>(a.hi + off) = *reinterpret_cast<const uint4*>(h);
+	if (a.lo) {
+		__half2 l[4];
+#pragma unroll
+		for (int i = 0; i < 4; i++) {
+			const float2 f = __half22float2(h[i]);
+			l[i] = __floats2half2_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+		}
+		*reinterpret_cast<uint4*>(a.lo + off) = *reinterpret_cast<const uint4*>(l);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// weights -> B tiles: element (row, k) of a WMat in ANY of the decode layouts -> fp16
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ld_h(const uint8_t* p) { return __half2float(*reinterpret_cast<const __half*>(p)); }
+
+// 8 consecutive elements k0..k0+7 (k0 % 8 == 0) of physical row `r`
+__device__ inline void wmat_decode8(const WMat& w, int r, int k0, float (&v)[8]) {
+	const int t = w.type;
+	const uint8_t* row = w.p0 + (size_t) r * w.s0;
+	switch (t) {
+		case XALM_F32: {
+			const float4 a = *reinterpret_cast<const float4*>(row + (size_t) k0 * 4);
+			const float4 b = *reinterpret_cast<const float4*>(row + (size_t) k0 * 4 + 16);
+			v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+			return;
+		}
+		case XALM_F16: case XALM_BF16: {
+			const uint4 q = *reinterpret_cast<const uint4*>(row + (size_t) k0 * 2);
+			const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+			for (int i = 0; i < 4; i++) {
+				if (t == XALM_F16) {
+					const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[i]));
+					v[2 * i] = f.x; v[2 * i + 1] = f.y;
+				} else {
+					v[2 * i] = __uint_as_float(u[i] << 16); v[2 * i + 1] = __uint_as_float(u[i] & 0xFFFF0000u);
+				}
+			}
+			return;
+		}
+		case XALM_F8_E2M5: case XALM_F8_E3M4: case XALM_F8_E4M3: case XALM_F8_E5M2: case XALM_U8: case XALM_Q8: case XALM_QI8: {
+			const uint2 q = *reinterpret_cast<const uint2*>(row + k0);
+			const uint32_t u[2] = {q.x, q.y};
+#pragma unroll
+			for (int i = 0; i < 8; i++) {
+				uint8_t b = (uint8_t) (u[i >> 2] >> (8 * (i & 3)));
+				if (t == XALM_Q8) b ^= 0x80; // stored biased on the device (formats.cuh)
+				v[i] = decode_byte_type(t, b);
+			}
+			return;
+		}
+		case XALM_TQ1_0: {
+			const uint8_t* blk = row + (size_t) (k0 / 256) * 54;
+#pragma unroll
+			for (int i = 0; i < 8; i++) v[i] = decode_block_elem(t, blk, (k0 % 256) + i);
+			return;
+		}
+	}
+	// ---- 32-element block formats: locate main bytes / scales / high bits in the unit-interleaved or planar layout ----
+	const int blk = k0 / 32, j0 = k0 % 32;
+	const uint8_t *mainp, *scp, *qhp = nullptr;
+	const int sc_bytes = (t == XALM_Q4_1 || t == XALM_Q5_1) ? 4 : 2;
+	const int main_per_blk = t == XALM_Q8_0 ? 32 : 16;
+	if (w.layout_units) {
+		const int ub = t == XALM_Q8_0 ? 272 : t == XALM_Q4_0 ? 144 : t == XALM_Q4_1 ? 160 : t == XALM_Q5_0 ? 176 : 192;
+		const uint8_t* unit = row + (size_t) (k0 / 256) * ub;
+		const int b = blk & 7;
+		const int main_bytes = main_per_blk * 8;
+		mainp = unit + b * main_per_blk;
+		scp = unit + main_bytes + b * sc_bytes;
+		if (t == XALM_Q5_0) qhp = unit + 144 + 4 * b;
+		if (t == XALM_Q5_1) qhp = unit + 160 + 4 * b;
+	} else {
+		mainp = row + (size_t) blk * main_per_blk;
+		scp = w.p1 + (size_t) r * w.s1 + (size_t) blk * sc_bytes;
+		if (w.p2) qhp = w.p2 + (size_t) r * w.s2 + (size_t) blk * 4;
+	}
+	const float d = ld_h(scp);
+	if (t == XALM_Q8_0) {
+		const uint2 q = *reinterpret_cast<const uint2*>(mainp + j0);
+		const uint32_t u[2] = {q.x, q.y};
+#pragma unroll
+		for (int i = 0; i < 8; i++) v[i] = __fmul_rn(d, (float) ((int) ((u[i >> 2] >> (8 * (i & 3))) & 0xFF) - 128));
+		return;
+	}
+	const float mn = sc_bytes == 4 ? ld_h(scp + 2) : 0.f;
+	const uint2 q = *reinterpret_cast<const uint2*>(mainp + (j0 & 15)); // nibble bytes of elements j0..j0+7 (low half: j < 16)
+	const uint32_t u[2] = {q.x, q.y};
+	const uint32_t qh = qhp ? *reinterpret_cast<const uint32_t*>(qhp) : 0u;
+#pragma unroll
+	for (int i = 0; i < 8; i++) {
+		const uint32_t byte = (u[i >> 2] >> (8 * (i & 3))) & 0xFF;
+		int qv = (j0 < 16) ? (int) (byte & 0x0F) : (int) (byte >> 4);
+		if (qhp) qv |= (int) ((qh >> (j0 + i)) & 1u) << 4;
+		switch (t) {
+			case XALM_Q4_0: v[i] = __fmul_rn(d, (float) (qv - 8)); break;
+			case XALM_Q5_0: v[i] = __fmul_rn(d, (float) (qv - 16)); break;
+			default: v[i] = __fadd_rn(__fmul_rn(d, (float) qv), mn); break; // Q4_1, Q5_1
+		}
+	}
+}
+
+// One thread per 16-byte chunk of the destination, in destination order (coalesced stores).  Destination row n of
+// B tile `nt`: plain matrices -> physical row nt*256 + n;  GLU (glu_off > 0 or glu) -> n < 128: W1 row nt*128 + n,
+// else W3 row glu_off + nt*128 + (n-128), so gate and up of the same hidden unit land in one accumulator row block.
+__global__ void dequant_tiles_kernel(const WMat w, int glu, int glu_off, int n_valid, int K, int NT, int KT, uint8_t* __restrict__ dst) {
+	const size_t chunks_per_tile = B_TILE_BYTES / 16;
+	const size_t total = (size_t) NT * KT * chunks_per_tile;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+		const size_t tile = i / chunks_per_tile;
+		const int ci = (int) (i % chunks_per_tile);
+		const int nt = (int) (tile / KT), kt = (int) (tile % KT);
+		const int r = (ci >> 6) * 8 + ((ci & 63) >> 3);
+		const int lc = (ci & 7) ^ (r & 7);
+		const int k0 = kt * GB_K + lc * 8;
+		int prow;
+		bool valid;
+		if (glu) {
+			const int o = nt * (GB_N / 2) + (r % (GB_N / 2));
+			valid = o < n_valid;
+			prow = r < GB_N / 2 ? o : glu_off + o;
+		} else {
+			prow = nt * GB_N + r;
+			valid = prow < n_valid;
+		}
+		uint4 out = make_uint4(0, 0, 0, 0);
+		if (valid && k0 < K) {
+			float v[8];
+			wmat_decode8(w, prow, k0, v);
+			__half2 h[4];
+#pragma unroll
+			for (int j = 0; j < 4; j++) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+			out = *reinterpret_cast<const uint4*>(h);
+		}
+		*reinterpret_cast<uint4*>(dst + i * 16) = out;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier, bulk copy, tcgen05
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(uint64_t* bar, uint32_t count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mb_expect_tx(uint64_t* bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_arrive(uint64_t* bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mb_wait(uint64_t* bar, uint32_t parity) {
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "WAIT_%=:\n"
+	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+	    "@p bra DONE_%=;\n"
+	    "bra WAIT_%=;\n"
+	    "DONE_%=:\n"
+	    "}\n" ::"r"(s_u32(bar)),
+	    "r"(parity)
+	    : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s_u32(dst)), "l"(src),
+	             "r"(bytes), "r"(s_u32(bar))
+	             : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// whole warp: allocate `cols` TMEM columns (power of two >= 32), base address -> *slot (shared memory)
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t cols) {
+	asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s_u32(slot)), "r"(cols) : "memory");
+	asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+	asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, fp16 operands, fp32 accumulate; issued by ONE thread for the CTA
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "setp.ne.b32 p, %4, 0;\n"
+	    "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+	    "}\n" ::"r"(tmem_d),
+	    "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+	    : "memory");
+}
+// all MMAs issued so far by this thread -> one arrival on `bar` when they have completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row atoms 1024 bytes apart (SBO), sm_100 descriptor version 1
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
+	return (uint64_t) ((saddr & 0x3FFFFu) >> 4) | ((uint64_t) (1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor, kind::f16: D fp32 (bits 4-5 = 1), A/B fp16 (0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__host__ __device__ constexpr uint32_t instr_desc_f16(int M, int N) {
+	return (1u << 4) | ((uint32_t) (N >> 3) << 17) | ((uint32_t) (M >> 4) << 24);
+}
+// 32 lanes x 16 consecutive fp32 columns of this warp's TMEM quadrant
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+	uint32_t r[16];
+	__syncwarp(); // .sync.aligned: the whole warp, converged
+	asm volatile(
+	    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+	    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+	      "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+	    : "r"(taddr));
+	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+	for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+	uint32_t r[8];
+	__syncwarp();
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+	             : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+	             : "r"(taddr));
+	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+	for (int i = 0; i < 8; i++) v[i] = __uint_as_float(r[i]);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// the GEMM: out(M, N) = A(M, K) . B(N, K)^T, persistent warp-specialised CTAs, one per SM
+//   warp 0    producer: one lane issues cp.async.bulk for the A tile(s) + B tile of each K step into a ring of NS stages
+//   warp 1    allocates TMEM; one lane issues tcgen05.mma (4 x K=16 per stage, x NA activation planes) and commits
+//   warps 2-5 epilogue: tcgen05.ld the 128 x 256 fp32 accumulator (one TMEM lane quadrant per warp) and apply the
+//             fused epilogue, while the MMA warp already fills the OTHER accumulator buffer (2 x 256 of the 512 columns)
+// ------------------------------------------------------------------------------------------------------------------
+enum { GEPI_STORE = 0, GEPI_RESID = 1, GEPI_GLU = 2, GEPI_QKV = 3 };
+
+struct GemmArgs {
+	const uint8_t* a_hi;
+	const uint8_t* a_lo;
+	const uint8_t* b;
+	int MT, NT, KT;     // tile counts; M tiles are [mt0, mt0 + MT)
+	int mt0;
+	int M;              // valid rows
+	int N;              // valid outputs (GLU: hidden units; else columns)
+	int epi;
+	float* out;         // STORE / RESID: row-major, leading dimension ldo, row index (m - out_row0)
+	int ldo;
+	int out_row0;
+	// QKV
+	__half* q_out;      // (T, q_dim) row-major fp16, RoPE applied
+	__half* k_cache;
+	__half* v_cache;
+	const float* rope_freq;
+	int q_dim, kv_dim, head_dim, pos0;
+	float qkv_clip;
+	// GLU
+	ATiles o;
+	int act;
+};
+
+constexpr int GEMM_THREADS = 192;
+template <int NA>
+struct GemmCfg {
+	static constexpr int STAGE = NA * A_TILE_BYTES + B_TILE_BYTES;
+	static constexpr int NS = NA == 1 ? 4 : 3;
+	static constexpr size_t SMEM = (size_t) NS * STAGE + 1024 /* alignment slack */ + 256 /* barriers */;
+};
+
+template <int NA>
+__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmArgs g) {
+	using Cfg = GemmCfg<NA>;
+	constexpr int NS = Cfg::NS;
+	extern __shared__ uint8_t smem_raw[];
+	// 1024-byte alignment in the SHARED address space (the swizzle pattern is a function of the address bits)
+	const uint32_t raw_s = s_u32(smem_raw);
+	uint8_t* smem = smem_raw + (((raw_s + 1023u) & ~1023u) - raw_s);
+	uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t) NS * Cfg::STAGE);
+	uint64_t* empty = full + NS;
+	uint64_t* tfull = empty + NS;   // [2] accumulator ready
+	uint64_t* tempty = tfull + 2;   // [2] accumulator drained
+	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	if (threadIdx.x == 0) {
+		for (int s = 0; s < NS; s++) {
+			mb_init(&full[s], 1);
+			mb_init(&empty[s], 1);
+		}
+		for (int i = 0; i < 2; i++) {
+			mb_init(&tfull[i], 1);
+			mb_init(&tempty[i], 4);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	if (warp == 1) tmem_alloc(tmem_slot, 512);
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+
+	const int n_tiles = g.MT * g.NT;
+	const int KT = g.KT;
+
+	if (warp == 0) {
+		if (lane == 0) {
+			int slot = 0, phase = 0;
+			for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+				const int mt = g.mt0 + tile % g.MT, nt = tile / g.MT;
+				const uint8_t* ah = g.a_hi + (size_t) mt * KT * A_TILE_BYTES;
+				const uint8_t* al = NA == 2 ? g.a_lo + (size_t) mt * KT * A_TILE_BYTES : nullptr;
+				const uint8_t* bt = g.b + (size_t) nt * KT * B_TILE_BYTES;
+				for (int kt = 0; kt < KT; kt++) {
+					mb_wait(&empty[slot], phase ^ 1);
+					uint8_t* st = smem + (size_t) slot * Cfg::STAGE;
+					mb_expect_tx(&full[slot], Cfg::STAGE);
+					bulk_load(st, ah + (size_t) kt * A_TILE_BYTES, A_TILE_BYTES, &full[slot]);
+					if (NA == 2) bulk_load(st + A_TILE_BYTES, al + (size_t) kt * A_TILE_BYTES, A_TILE_BYTES, &full[slot]);
+					bulk_load(st + NA * A_TILE_BYTES, bt + (size_t) kt * B_TILE_BYTES, B_TILE_BYTES, &full[slot]);
+					if (++slot == NS) { slot = 0; phase ^= 1; }
+				}
+			}
+		}
+		__syncwarp();
+	} else if (warp == 1) {
+		if (lane == 0) {
+			constexpr uint32_t idesc = instr_desc_f16(GB_M, GB_N);
+			int slot = 0, phase = 0, acc = 0, acc_phase = 0;
+			for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+				mb_wait(&tempty[acc], acc_phase ^ 1);
+				tc_fence_after();
+				const uint32_t d_tmem = tmem_base + (uint32_t) acc * GB_N;
+				for (int kt = 0; kt < KT; kt++) {
+					mb_wait(&full[slot], phase);
+					tc_fence_after();
+					const uint32_t sa = s_u32(smem + (size_t) slot * Cfg::STAGE);
+					const uint64_t bdesc = smem_desc(sa + NA * A_TILE_BYTES);
+#pragma unroll
+					for (int p = 0; p < NA; p++) {
+						const uint64_t adesc = smem_desc(sa + p * A_TILE_BYTES);
+#pragma unroll
+						for (int k = 0; k < GB_K / UMMA_K; k++) {
+							// advancing K by 16 fp16 = 32 bytes inside the 128-byte swizzle row: +2 in the (>>4) address field
+							umma_f16(d_tmem, adesc + (uint64_t) (2 * k), bdesc + (uint64_t) (2 * k), idesc, (uint32_t) ((kt | k | p) != 0));
+						}
+					}
+					umma_commit(&empty[slot]); // frees the stage once these MMAs have read it
+					if (++slot == NS) { slot = 0; phase ^= 1; }
+				}
+				umma_commit(&tfull[acc]);
+				acc ^= 1;
+				if (acc == 0) acc_phase ^= 1;
+			}
+		}
+		__syncwarp();
+	} else {
+		const int quad = warp & 3; // TMEM lanes [32*quad, 32*quad+32) are the ones this warp may read
+		int acc = 0, acc_phase = 0;
+		for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+			const int mt = g.mt0 + tile % g.MT, nt = tile / g.MT;
+			mb_wait(&tfull[acc], acc_phase);
+			tc_fence_after();
+			const int m = mt * GB_M + quad * 32 + lane;
+			const bool mrow = m < g.M;
+			const uint32_t taddr = tmem_base + ((uint32_t) (quad * 32) << 16) + (uint32_t) acc * GB_N;
+			if (g.epi == GEPI_GLU) {
+				for (int c = 0; c < GB_N / 2; c += 8) {
+					float gt[8], up[8];
+					tmem_ld8(taddr + c, gt);
+					tmem_ld8(taddr + GB_N / 2 + c, up);
+					const int o0 = nt * (GB_N / 2) + c;
+					if (mrow && o0 < g.N) {
+						float h[8];
+#pragma unroll
+						for (int i = 0; i < 8; i++) h[i] = (g.act == XALM_SILU ? act_silu(gt[i]) : act_gelu(gt[i])) * up[i]; // infer.cpp:470-488
+						store_a8(g.o, m, o0, h);
+					}
+				}
+			} else {
+				for (int c = 0; c < GB_N; c += 16) {
+					float v[16];
+					tmem_ld16(taddr + c, v);
+					const int n0 = nt * GB_N + c;
+					if (!mrow || n0 >= g.N) continue;
+					if (g.epi == GEPI_QKV) {
+						const int pos = g.pos0 + m;
+#pragma unroll
+						for (int i = 0; i < 16; i += 2) {
+							const int n = n0 + i;
+							if (n >= g.N) break;
+							float v0 = clipf(v[i], g.qkv_clip), v1 = clipf(v[i + 1], g.qkv_clip); // infer.cpp:389-399
+							if (n < g.q_dim) {
+								rope_pair(v0, v1, n % g.head_dim, pos, g.rope_freq);
+								*reinterpret_cast<__half2*>(g.q_out + (size_t) m * g.q_dim + n) = __floats2half2_rn(v0, v1);
+							} else if (n < g.q_dim + g.kv_dim) {
+								const int j = n - g.q_dim;
+								rope_pair(v0, v1, j % g.head_dim, pos, g.rope_freq);
+								*reinterpret_cast<__half2*>(g.k_cache + (size_t) pos * g.kv_dim + j) = __floats2half2_rn(v0, v1);
+							} else {
+								const int j = n - g.q_dim - g.kv_dim;
+								*reinterpret_cast<__half2*>(g.v_cache + (size_t) pos * g.kv_dim + j) = __floats2half2_rn(v0, v1);
+							}
+						}
+					} else {
+						float* o = g.out + (size_t) (m - g.out_row0) * g.ldo + n0;
+#pragma unroll
+						for (int i = 0; i < 16; i += 4) {
+							if (n0 + i >= g.N) break;
+							float4 r = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+							if (g.epi == GEPI_RESID) {
+								const float4 x = *reinterpret_cast<const float4*>(o + i);
+								r.x += x.x; r.y += x.y; r.z += x.z; r.w += x.w; // infer.cpp:450-452, :492-494
+							}
+							*reinterpret_cast<float4*>(o + i) = r;
+						}
+					}
+				}
+			}
+			tc_fence_before();
+			__syncwarp();
+			if (lane == 0) mb_arrive(&tempty[acc]);
+			acc ^= 1;
+			if (acc == 0) acc_phase ^= 1;
+		}
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 1) {
+		tc_fence_after();
+		tmem_dealloc(tmem_base, 512);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// row-wise kernels
+// ------------------------------------------------------------------------------------------------------------------
+// _copy_embedding (infer.cpp:553-602) for T tokens
+__global__ void embed_rows_kernel(int type, const uint8_t* __restrict__ table, size_t row_bytes, int dim, const int* __restrict__ tokens, int T,
+                                  float* __restrict__ x) {
+	const size_t total = (size_t) T * dim;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+		const int m = (int) (i / dim), j = (int) (i % dim);
+		x[i] = decode_disk_elem(type, table + (size_t) tokens[m] * row_bytes, (size_t) j);
+	}
+}
+
+// rmsnorm (infer.cpp:224-236) of each row, result as an A-tile operand.  One warp per row.
+__global__ void rmsnorm_rows_kernel(const float* __restrict__ x, int T, int dim, const uint8_t* __restrict__ w, int wtype, float eps, ATiles o) {
+	const int warps = blockDim.x >> 5;
+	const int lane = threadIdx.x & 31;
+	for (int m = blockIdx.x * warps + (threadIdx.x >> 5); m < T; m += gridDim.x * warps) {
+		const float* xr = x + (size_t) m * dim;
+		float ss = 0.f;
+		for (int j = lane * 4; j < dim; j += 128) {
+			const float4 v = *reinterpret_cast<const float4*>(xr + j);
+			ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+		}
+		ss = warp_sum(ss);
+		const float scale = 1.0f / sqrtf(ss / (float) dim + eps);
+		for (int j = lane * 8; j < dim; j += 256) {
+			float v[8];
+#pragma unroll
+			for (int i = 0; i < 8; i++) {
+				const float gw = wtype == XALM_F32 ? reinterpret_cast<const float*>(w)[j + i]
+				                                   : bf16_bits_to_f32(reinterpret_cast<const uint16_t*>(w)[j + i]);
+				v[i] = xr[j + i] * scale * gw; // infer.cpp:233-235
+			}
+			store_a8(o, m, j, v);
+		}
+	}
+}
+
+// Sampler::sample_prob (sampler.cpp:18-33) per row: softmax(logits)[target], the FLT_MIN-seeded max included
+__global__ void target_prob_kernel(const float* __restrict__ logits, int vocab, const int* __restrict__ targets, float* __restrict__ probs) {
+	__shared__ float red[32];
+	const float* l = logits + (size_t) blockIdx.x * vocab;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+	float mx = FLT_MIN;
+	for (int i = threadIdx.x; i < vocab; i += blockDim.x) mx = fmaxf(mx, l[i]);
+	mx = warp_max(mx);
+	if (lane == 0) red[warp] = mx;
+	__syncthreads();
+	mx = red[0];
+	for (int i = 1; i < nw; i++) mx = fmaxf(mx, red[i]);
+	__syncthreads();
+	float sum = 0.f;
+	for (int i = threadIdx.x; i < vocab; i += blockDim.x) sum += expf(l[i] - mx);
+	sum = warp_sum(sum);
+	if (lane == 0) red[warp] = sum;
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		float tot = 0.f;
+		for (int i = 0; i < nw; i++) tot += red[i];
+		probs[blockIdx.x] = expf(l[targets[blockIdx.x]] - mx) / tot;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// causal attention over the fp16 KV cache for a block of 64 query rows of one head (attn + softmax, infer.cpp:325-359,
+// 280-297, for T rows at once).  Flash-style: S = Q K^T and O += P V on mma.sync m16n8k16 tiles (fp16 in, fp32 out),
+// online softmax in fp32 with expf.  Query row i (position pos0+i) sees cache rows [0, pos0+i].
+// Not a tcgen05 kernel: attention is ~7 % of the prefill flops at 4k; the GEMMs above are where the tensor time goes.
+// ------------------------------------------------------------------------------------------------------------------
+struct AttnPArgs {
+	const __half* q;       // (T, q_dim)
+	const __half* k_cache; // (max_seq_len, kv_dim)
+	const __half* v_cache;
+	ATiles o;              // xb2
+	int T, pos0, q_dim, kv_dim, n_heads, n_kv_heads, n_qt;
+};
+
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t saddr) {
+	asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void ldsm4_t(uint32_t (&r)[4], uint32_t saddr) {
+	asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+	asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+	             : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+	             : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void* g, bool valid) {
+	const int sz = valid ? 16 : 0; // src-size 0 -> zero fill
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(g), "r"(sz) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+	const __half2 h = __floats2half2_rn(a, b);
+	return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <int HD>
+__global__ void __launch_bounds__(128) attn_prefill_kernel(const AttnPArgs a) {
+	constexpr int BQ = 64, BKV = 64;
+	constexpr int CPR = HD / 8;         // 16-byte chunks per row
+	constexpr int ROWB = HD * 2;        // bytes per row
+	extern __shared__ __align__(128) uint8_t sm[];
+	uint8_t* sQ = sm;
+	uint8_t* sK = sQ + BQ * ROWB;       // [2][BKV][HD]
+	uint8_t* sV = sK + 2 * BKV * ROWB;
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int qt = a.n_qt - 1 - (int) blockIdx.x; // longest (latest) query tiles first
+	const int h = blockIdx.y;
+	const int kvh = h / (a.n_heads / a.n_kv_heads);
+	const int q0 = qt * BQ;
+	const int q_last = min(q0 + BQ, a.T) - 1;
+	const int kv_total = a.pos0 + q_last + 1;  // cache rows any row of this tile may see
+	const int n_kb = (kv_total + BKV - 1) / BKV;
+	// chunk (r, c) lives at r*ROWB + ((c ^ (r & 7)) * 16): conflict-free for ldmatrix (8 rows x 16 bytes per phase)
+	auto soff = [](int r, int c) { return (uint32_t) (r * ROWB + ((c ^ (r & 7)) << 4)); };
+
+	// ---- async loads: Q once, K/V blocks double-buffered ----
+	for (int i = threadIdx.x; i < BQ * CPR; i += 128) {
+		const int r = i / CPR, c = i % CPR;
+		const bool ok = q0 + r < a.T;
+		cp_async16(s_u32(sQ) + soff(r, c), a.q + (size_t) (ok ? q0 + r : 0) * a.q_dim + h * HD + c * 8, ok);
+	}
+	auto load_kv = [&](int kb, int buf) {
+		for (int i = threadIdx.x; i < BKV * CPR; i += 128) {
+			const int r = i / CPR, c = i % CPR;
+			const int key = kb * BKV + r;
+			const bool ok = key < kv_total;
+			const size_t g = (size_t) (ok ? key : 0) * a.kv_dim + kvh * HD + c * 8;
+			cp_async16(s_u32(sK) + buf * BKV * ROWB + soff(r, c), a.k_cache + g, ok);
+			cp_async16(s_u32(sV) + buf * BKV * ROWB + soff(r, c), a.v_cache + g, ok);
+		}
+	};
+	load_kv(0, 0);
+	asm volatile("cp.async.commit_group;" ::: "memory");
+
+	float o_acc[HD / 8][4];
+#pragma unroll
+	for (int i = 0; i < HD / 8; i++)
+#pragma unroll
+		for (int j = 0; j < 4; j++) o_acc[i][j] = 0.f;
+	float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+	uint32_t qf[HD / 16][4];
+	const float scale = 1.0f / sqrtf((float) HD);
+	const int row_a = q0 + warp * 16 + (lane >> 2); // this thread's two query rows: row_a and row_a + 8
+	bool q_loaded = false;
+
+	for (int kb = 0; kb < n_kb; kb++) {
+		const int buf = kb & 1;
+		if (kb + 1 < n_kb) load_kv(kb + 1, buf ^ 1);
+		asm volatile("cp.async.commit_group;" ::: "memory");
+		asm volatile("cp.async.wait_group 1;" ::: "memory");
+		__syncthreads();
+		if (!q_loaded) {
+#pragma unroll
+			for (int ks = 0; ks < HD / 16; ks++) ldsm4(qf[ks], s_u32(sQ) + soff(warp * 16 + (lane & 15), ks * 2 + (lane >> 4)));
+			q_loaded = true;
+		}
+		// ---- S = Q K^T (16 query rows x 64 keys per warp) ----
+		float s[BKV / 8][4];
+#pragma unroll
+		for (int i = 0; i < BKV / 8; i++)
+#pragma unroll
+			for (int j = 0; j < 4; j++) s[i][j] = 0.f;
+		const uint32_t kbase = s_u32(sK) + buf * BKV * ROWB;
+#pragma unroll
+		for (int ks = 0; ks < HD / 16; ks++) {
+#pragma unroll
+			for (int nb = 0; nb < BKV / 16; nb++) {
+				uint32_t kf[4];
+				ldsm4(kf, kbase + soff(nb * 16 + (lane & 7) + ((lane >> 4) << 3), ks * 2 + ((lane >> 3) & 1)));
+				mma16816(s[2 * nb], qf[ks], kf[0], kf[1]);
+				mma16816(s[2 * nb + 1], qf[ks], kf[2], kf[3]);
+			}
+		}
+		// ---- scale, causal mask, online softmax ----
+		const bool need_mask = kb * BKV + BKV - 1 > a.pos0 + q0 + warp * 16; // some key of this block is beyond the warp's first row
+		float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+		for (int i = 0; i < BKV / 8; i++) {
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				float v = s[i][j] * scale;
+				if (need_mask) {
+					const int key = kb * BKV + i * 8 + 2 * (lane & 3) + (j & 1);
+					const int row = row_a + (j >> 1) * 8;
+					if (key > a.pos0 + row) v = -INFINITY;
+				}
+				s[i][j] = v;
+				mx[j >> 1] = fmaxf(mx[j >> 1], v);
+			}
+		}
+		float corr[2];
+#pragma unroll
+		for (int r = 0; r < 2; r++) {
+			mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+			mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+			const float m_new = fmaxf(m_run[r], mx[r]);
+			corr[r] = expf(m_run[r] - m_new); // first block: exp(-inf) = 0
+			m_run[r] = m_new;
+		}
+		float rs[2] = {0.f, 0.f};
+#pragma unroll
+		for (int i = 0; i < BKV / 8; i++) {
+#pragma unroll
+			for (int j = 0; j < 4; j++) {
+				const float p = expf(s[i][j] - m_run[j >> 1]);
+				s[i][j] = p;
+				rs[j >> 1] += p;
+			}
+		}
+#pragma unroll
+		for (int r = 0; r < 2; r++) l_run[r] = l_run[r] * corr[r] + rs[r]; // per-thread partial row sums, reduced over the quad at the end
+#pragma unroll
+		for (int i = 0; i < HD / 8; i++) {
+			o_acc[i][0] *= corr[0]; o_acc[i][1] *= corr[0];
+			o_acc[i][2] *= corr[1]; o_acc[i][3] *= corr[1];
+		}
+		// ---- O += P V ----
+		const uint32_t vbase = s_u32(sV) + buf * BKV * ROWB;
+#pragma unroll
+		for (int kk = 0; kk < BKV / 16; kk++) {
+			uint32_t pf[4];
+			pf[0] = pack_h2(s[2 * kk][0], s[2 * kk][1]);
+			pf[1] = pack_h2(s[2 * kk][2], s[2 * kk][3]);
+			pf[2] = pack_h2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
+			pf[3] = pack_h2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+#pragma unroll
+			for (int nb = 0; nb < HD / 16; nb++) {
+				uint32_t vf[4];
+				ldsm4_t(vf, vbase + soff(kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3), nb * 2 + (lane >> 4)));
+				mma16816(o_acc[2 * nb], pf, vf[0], vf[1]);
+				mma16816(o_acc[2 * nb + 1], pf, vf[2], vf[3]);
+			}
+		}
+		__syncthreads(); // everyone is done with `buf` before the next iteration's prefetch overwrites it
+	}
+	// ---- normalise and store as an A-tile operand (xb2) ----
+#pragma unroll
+	for (int r = 0; r < 2; r++) {
+		l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 1);
+		l_run[r] += __shfl_xor_sync(0xffffffffu, l_run[r], 2);
+	}
+#pragma unroll
+	for (int r = 0; r < 2; r++) {
+		const int row = row_a + r * 8;
+		if (row >= a.T) continue;
+		const float inv = 1.0f / l_run[r];
+#pragma unroll
+		for (int i = 0; i < HD / 8; i++) {
+			const float v0 = o_acc[i][2 * r] * inv, v1 = o_acc[i][2 * r + 1] * inv;
+			const int col = h * HD + i * 8 + 2 * (lane & 3);
+			const size_t off = a_off(row, col, a.o.KT);
+			const __half2 hh = __floats2half2_rn(v0, v1);
+			*reinterpret_cast<__half2*>(a.o.hi + off) = hh;
+			if (a.o.lo) {
+				const float2 f = __half22float2(hh);
+				*reinterpret_cast<__half2*>(a.o.lo + off) = __floats2half2_rn(v0 - f.x, v1 - f.y);
+			}
+		}
+	}
+}
+
+// fp32 row-major (T, K) -> A tiles (op-level hook and tests)
+__global__ void pack_a_kernel(const float* __restrict__ a, int T, int K, ATiles o) {
+	const size_t total = (size_t) T * (K / 8);
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+		const int m = (int) (i / (K / 8)), k0 = (int) (i % (K / 8)) * 8;
+		float v[8];
+#pragma unroll
+		for (int j = 0; j < 8; j++) v[j] = a[(size_t) m * K + k0 + j];
+		store_a8(o, m, k0, v);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------------
+static int g_sms = 0;
+static int sm_count() {
+	if (!g_sms) {
+		int dev = 0;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+		if (g_sms <= 0) g_sms = 148;
+	}
+	return g_sms;
+}
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+struct DevBuf {
+	uint8_t* p = nullptr;
+	size_t cap = 0;
+	int ensure(size_t bytes, bool zero, cudaStream_t s) {
+		if (bytes <= cap) return XALM_OK;
+		if (p) {
+			XALM_CUDA_CHECK(cudaStreamSynchronize(s));
+			XALM_CUDA_CHECK(cudaFree(p));
+			p = nullptr; cap = 0;
+		}
+		XALM_CUDA_CHECK(cudaMalloc((void**) &p, bytes));
+		cap = bytes;
+		if (zero) XALM_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, s));
+		return XALM_OK;
+	}
+	void release() {
+		if (p) cudaFree(p);
+		p = nullptr; cap = 0;
+	}
+};
+
+struct PrefillScratch {
+	DevBuf x, xb_hi, xb_lo, xb2_hi, xb2_lo, hb_hi, hb_lo, q, wt, logits, tokens, targets, probs;
+	int logits_rows = 0;
+	int attn_smem_set = 0;
+	bool gemm_attr_set[3] = {false, false, false};
+};
+
+void prefill_free(PrefillScratch* s) {
+	if (!s) return;
+	DevBuf* all[] = {&s->x, &s->xb_hi, &s->xb_lo, &s->xb2_hi, &s->xb2_lo, &s->hb_hi, &s->hb_lo, &s->q, &s->wt, &s->logits, &s->tokens, &s->targets, &s->probs};
+	for (DevBuf* b : all) b->release();
+	delete s;
+}
+const float* prefill_logits_dev(const PrefillScratch* s, int* rows) {
+	if (rows) *rows = s ? s->logits_rows : 0;
+	return s ? reinterpret_cast<const float*>(s->logits.p) : nullptr;
+}
+
+static bool g_gemm_attr[3] = {false, false, false};
+static int launch_gemm(const GemmArgs& g, int na, cudaStream_t s) {
+	const int tiles = g.MT * g.NT;
+	if (tiles <= 0) return XALM_OK;
+	const int grid = std::min(tiles, sm_count());
+	cudaError_t e;
+	if (na == 2) {
+		if (!g_gemm_attr[2]) {
+			XALM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) GemmCfg<2>::SMEM));
+			g_gemm_attr[2] = true;
+		}
+		gemm_tc_kernel<2><<<grid, GEMM_THREADS, GemmCfg<2>::SMEM, s>>>(g);
+	} else {
+		if (!g_gemm_attr[1]) {
+			XALM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) GemmCfg<1>::SMEM));
+			g_gemm_attr[1] = true;
+		}
+		gemm_tc_kernel<1><<<grid, GEMM_THREADS, GemmCfg<1>::SMEM, s>>>(g);
+	}
+	e = cudaGetLastError();
+	if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "gemm_tc launch failed: %s", cudaGetErrorString(e));
+	return XALM_OK;
+}
+
+// weights of `w` (rows [0, n_valid) or the GLU pairing) -> B tiles in `dst`
+static int launch_dequant_tiles(const WMat& w, bool glu, int glu_off, int n_valid, int K, int NT, int KT, uint8_t* dst, cudaStream_t s) {
+	const size_t chunks = (size_t) NT * KT * (B_TILE_BYTES / 16);
+	const int grid = (int) std::min<size_t>((chunks + 255) / 256, (size_t) sm_count() * 16);
+	dequant_tiles_kernel<<<grid, 256, 0, s>>>(w, glu ? 1 : 0, glu_off, n_valid, K, NT, KT, dst);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "dequant_tiles launch failed: %s", cudaGetErrorString(e));
+	return XALM_OK;
+}
+
+static bool prefill_type_ok(int t) {
+	TypeInfo ti;
+	return type_info(t, &ti);
+}
+
+template <int HD>
+static int launch_attn_p(const AttnPArgs& a, cudaStream_t s) {
+	const size_t smem = (size_t) 64 * HD * 2 * 5;
+	static bool attr = false;
+	if (!attr) {
+		XALM_CUDA_CHECK(cudaFuncSetAttribute(attn_prefill_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		attr = true;
+	}
+	attn_prefill_kernel<HD><<<dim3(a.n_qt, a.n_heads), 128, smem, s>>>(a);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "attn_prefill launch failed: %s", cudaGetErrorString(e));
+	return XALM_OK;
+}
+
+int prefill_run(const PrefillModel& pm, PrefillScratch** scratch, const int* tokens, int n, int pos0, int want_logits, float* logits_host,
+                const int* targets, float* probs_host, int split, int* n_launches) {
+	const xalm_config& c = pm.c;
+	if (n <= 0) return set_error(XALM_ERR_INVALID, "prefill: n = %d", n);
+	if (pos0 < 0 || (long long) pos0 + n > c.max_seq_len)
+		return set_error(XALM_ERR_INVALID, "prefill: positions [%d, %d) do not fit the %d-slot KV cache without wrapping (use forward)", pos0,
+		                 pos0 + n, c.max_seq_len);
+	if (c.head_dim != 64 && c.head_dim != 128) return set_error(XALM_ERR_UNSUPPORTED, "prefill: head_dim %d (64 or 128)", c.head_dim);
+	if (c.dim % 8 || c.hidden_dim % 8 || pm.q_dim % 8 || pm.kv_dim % 8) return set_error(XALM_ERR_UNSUPPORTED, "prefill: dims must be multiples of 8");
+	if (targets && want_logits != 2) return set_error(XALM_ERR_INVALID, "prefill: target probabilities need the logits of every position");
+	const int na = split == 2 ? 2 : 1;
+	cudaStream_t s = pm.stream;
+	if (!*scratch) *scratch = new PrefillScratch();
+	PrefillScratch& sc = **scratch;
+	int launches = 0;
+
+	const int T = n, MT = cdiv(T, GB_M), Tp = MT * GB_M;
+	const int KT_dim = cdiv(c.dim, GB_K), KT_q = cdiv(pm.q_dim, GB_K), KT_h = cdiv(c.hidden_dim, GB_K);
+	const int n_qkv = pm.q_dim + 2 * pm.kv_dim;
+	const int NT_qkv = cdiv(n_qkv, GB_N), NT_dim = cdiv(c.dim, GB_N), NT_glu = cdiv(c.hidden_dim, GB_N / 2), NT_cls = cdiv(c.vocab_size, GB_N);
+	// ---- scratch ----
+	XALM_TRY(sc.x.ensure((size_t) Tp * c.dim * 4, true, s));
+	XALM_TRY(sc.xb_hi.ensure((size_t) MT * KT_dim * A_TILE_BYTES, true, s));
+	XALM_TRY(sc.xb2_hi.ensure((size_t) MT * KT_q * A_TILE_BYTES, true, s));
+	XALM_TRY(sc.hb_hi.ensure((size_t) MT * KT_h * A_TILE_BYTES, true, s));
+	if (na == 2) {
+		XALM_TRY(sc.xb_lo.ensure((size_t) MT * KT_dim * A_TILE_BYTES, true, s));
+		XALM_TRY(sc.xb2_lo.ensure((size_t) MT * KT_q * A_TILE_BYTES, true, s));
+		XALM_TRY(sc.hb_lo.ensure((size_t) MT * KT_h * A_TILE_BYTES, true, s));
+	}
+	XALM_TRY(sc.q.ensure((size_t) Tp * pm.q_dim * 2, true, s));
+	size_t wt_bytes = std::max({(size_t) NT_qkv * KT_dim, (size_t) NT_dim * KT_q, (size_t) NT_glu * KT_dim, (size_t) NT_dim * KT_h}) * B_TILE_BYTES;
+	if (want_logits) wt_bytes = std::max(wt_bytes, (size_t) NT_cls * KT_dim * B_TILE_BYTES);
+	XALM_TRY(sc.wt.ensure(wt_bytes, false, s));
+	XALM_TRY(sc.tokens.ensure((size_t) T * 4, false, s));
+	// want 1: only the last M tile goes through the classifier; its valid rows are stored, the last one is the answer
+	const int logit_row0 = want_logits == 1 ? (MT - 1) * GB_M : 0;
+	const int logit_rows = want_logits ? T - logit_row0 : 0;
+	if (logit_rows) XALM_TRY(sc.logits.ensure((size_t) logit_rows * c.vocab_size * 4, false, s));
+	sc.logits_rows = logit_rows;
+
+	ATiles xb{sc.xb_hi.p, na == 2 ? sc.xb_lo.p : nullptr, KT_dim};
+	ATiles xb2{sc.xb2_hi.p, na == 2 ? sc.xb2_lo.p : nullptr, KT_q};
+	ATiles hb{sc.hb_hi.p, na == 2 ? sc.hb_lo.p : nullptr, KT_h};
+	float* x = reinterpret_cast<float*>(sc.x.p);
+	__half* q = reinterpret_cast<__half*>(sc.q.p);
+
+	for (int i = 0; i < T; i++)
+		if (tokens[i] < 0 || tokens[i] >= c.vocab_size) return set_error(XALM_ERR_INVALID, "prefill: token %d out of range", tokens[i]);
+	XALM_CUDA_CHECK(cudaMemcpyAsync(sc.tokens.p, tokens, (size_t) T * 4, cudaMemcpyHostToDevice, s));
+	embed_rows_kernel<<<std::min(cdiv(T * c.dim, 256), sm_count() * 8), 256, 0, s>>>(pm.embed_type, pm.embed_raw, pm.embed_row_bytes, c.dim,
+	                                                                                  reinterpret_cast<const int*>(sc.tokens.p), T, x);
+	launches++;
+	const int norm_grid = std::min(cdiv(T, 8), sm_count() * 4);
+	for (size_t l = 0; l < pm.layers.size(); l++) {
+		const PrefillLayer& L = pm.layers[l];
+		if (!prefill_type_ok(L.wqkv.type)) return set_error(XALM_ERR_UNSUPPORTED, "prefill: weight type %d", L.wqkv.type);
+		// ---- attention half ----
+		rmsnorm_rows_kernel<<<norm_grid, 256, 0, s>>>(x, T, c.dim, L.rms_att, L.rms_att_type, c.norm_eps, xb);
+		XALM_TRY(launch_dequant_tiles(L.wqkv, false, 0, n_qkv, c.dim, NT_qkv, KT_dim, sc.wt.p, s));
+		GemmArgs g = {};
+		g.a_hi = xb.hi; g.a_lo = xb.lo; g.b = sc.wt.p;
+		g.MT = MT; g.NT = NT_qkv; g.KT = KT_dim; g.mt0 = 0; g.M = T; g.N = n_qkv; g.epi = GEPI_QKV;
+		g.q_out = q; g.k_cache = L.k_cache; g.v_cache = L.v_cache; g.rope_freq = pm.rope_freq;
+		g.q_dim = pm.q_dim; g.kv_dim = pm.kv_dim; g.head_dim = c.head_dim; g.pos0 = pos0; g.qkv_clip = c.qkv_clip;
+		XALM_TRY(launch_gemm(g, na, s));
+		AttnPArgs at = {q, L.k_cache, L.v_cache, xb2, T, pos0, pm.q_dim, pm.kv_dim, c.n_heads, c.n_kv_heads, cdiv(T, 64)};
+		if (c.head_dim == 128) XALM_TRY(launch_attn_p<128>(at, s));
+		else XALM_TRY(launch_attn_p<64>(at, s));
+		XALM_TRY(launch_dequant_tiles(L.wo, false, 0, c.dim, pm.q_dim, NT_dim, KT_q, sc.wt.p, s));
+		g = {};
+		g.a_hi = xb2.hi; g.a_lo = xb2.lo; g.b = sc.wt.p;
+		g.MT = MT; g.NT = NT_dim; g.KT = KT_q; g.M = T; g.N = c.dim; g.epi = GEPI_RESID; g.out = x; g.ldo = c.dim;
+		XALM_TRY(launch_gemm(g, na, s));
+		// ---- feed-forward half ----
+		rmsnorm_rows_kernel<<<norm_grid, 256, 0, s>>>(x, T, c.dim, L.rms_ffn, L.rms_ffn_type, c.norm_eps, xb);
+		XALM_TRY(launch_dequant_tiles(L.w13, true, L.glu_off, c.hidden_dim, c.dim, NT_glu, KT_dim, sc.wt.p, s));
+		g = {};
+		g.a_hi = xb.hi; g.a_lo = xb.lo; g.b = sc.wt.p;
+		g.MT = MT; g.NT = NT_glu; g.KT = KT_dim; g.M = T; g.N = c.hidden_dim; g.epi = GEPI_GLU; g.o = hb; g.act = c.act;
+		XALM_TRY(launch_gemm(g, na, s));
+		XALM_TRY(launch_dequant_tiles(L.w2, false, 0, c.dim, c.hidden_dim, NT_dim, KT_h, sc.wt.p, s));
+		g = {};
+		g.a_hi = hb.hi; g.a_lo = hb.lo; g.b = sc.wt.p;
+		g.MT = MT; g.NT = NT_dim; g.KT = KT_h; g.M = T; g.N = c.dim; g.epi = GEPI_RESID; g.out = x; g.ldo = c.dim;
+		XALM_TRY(launch_gemm(g, na, s));
+		launches += 11;
+	}
+	if (want_logits) {
+		rmsnorm_rows_kernel<<<norm_grid, 256, 0, s>>>(x, T, c.dim, pm.rms_final, pm.rms_final_type, c.norm_eps, xb);
+		XALM_TRY(launch_dequant_tiles(pm.wcls, false, 0, c.vocab_size, c.dim, NT_cls, KT_dim, sc.wt.p, s));
+		GemmArgs g = {};
+		g.a_hi = xb.hi; g.a_lo = xb.lo; g.b = sc.wt.p;
+		g.NT = NT_cls; g.KT = KT_dim; g.M = T; g.N = c.vocab_size; g.epi = GEPI_STORE;
+		g.out = reinterpret_cast<float*>(sc.logits.p); g.ldo = c.vocab_size;
+		g.mt0 = want_logits == 1 ? MT - 1 : 0;
+		g.MT = want_logits == 1 ? 1 : MT;
+		g.out_row0 = logit_row0;
+		XALM_TRY(launch_gemm(g, na, s));
+		launches += 3;
+		cudaError_t e = cudaGetLastError();
+		if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "prefill launch failed: %s", cudaGetErrorString(e));
+		if (targets && probs_host) {
+			XALM_TRY(sc.targets.ensure((size_t) T * 4, false, s));
+			XALM_TRY(sc.probs.ensure((size_t) T * 4, false, s));
+			for (int i = 0; i < T; i++)
+				if (targets[i] < 0 || targets[i] >= c.vocab_size) return set_error(XALM_ERR_INVALID, "prefill: target %d out of range", targets[i]);
+			XALM_CUDA_CHECK(cudaMemcpyAsync(sc.targets.p, targets, (size_t) T * 4, cudaMemcpyHostToDevice, s));
+			target_prob_kernel<<<T, 256, 0, s>>>(reinterpret_cast<const float*>(sc.logits.p), c.vocab_size, reinterpret_cast<const int*>(sc.targets.p),
+			                                     reinterpret_cast<float*>(sc.probs.p));
+			launches++;
+			XALM_CUDA_CHECK(cudaMemcpyAsync(probs_host, sc.probs.p, (size_t) T * 4, cudaMemcpyDeviceToHost, s));
+		}
+		if (logits_host) {
+			if (want_logits == 2)
+				XALM_CUDA_CHECK(cudaMemcpyAsync(logits_host, sc.logits.p, (size_t) T * c.vocab_size * 4, cudaMemcpyDeviceToHost, s));
+			else
+				XALM_CUDA_CHECK(cudaMemcpyAsync(logits_host, sc.logits.p + (size_t) (sc.logits_rows - 1) * c.vocab_size * 4, (size_t) c.vocab_size * 4,
+				                                cudaMemcpyDeviceToHost, s));
+		}
+	}
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "prefill launch failed: %s", cudaGetErrorString(e));
+	if (n_launches) *n_launches = launches;
+	return XALM_OK;
+}
+
+// ---- op-level hook -----------------------------------------------------------------------------------------------------
+int prefill_gemm_dev(const WMat& w, const float* a_dev, int T, float* out_dev, int split, cudaStream_t s) {
+	const int K = w.n, N = w.rows;
+	if (K % 8) return set_error(XALM_ERR_INVALID, "gemm: K %% 8 != 0");
+	const int na = split == 2 ? 2 : 1;
+	const int MT = cdiv(T, GB_M), KT = cdiv(K, GB_K), NT = cdiv(N, GB_N);
+	DevBuf ah, al, bt;
+	XALM_TRY(ah.ensure((size_t) MT * KT * A_TILE_BYTES, true, s));
+	if (na == 2) XALM_TRY(al.ensure((size_t) MT * KT * A_TILE_BYTES, true, s));
+	XALM_TRY(bt.ensure((size_t) NT * KT * B_TILE_BYTES, false, s));
+	ATiles at{ah.p, na == 2 ? al.p : nullptr, KT};
+	pack_a_kernel<<<std::min(cdiv(T * (K / 8), 256), sm_count() * 8), 256, 0, s>>>(a_dev, T, K, at);
+	int rc = launch_dequant_tiles(w, false, 0, N, K, NT, KT, bt.p, s);
+	if (rc == XALM_OK) {
+		GemmArgs g = {};
+		g.a_hi = at.hi; g.a_lo = at.lo; g.b = bt.p;
+		g.MT = MT; g.NT = NT; g.KT = KT; g.M = T; g.N = N; g.epi = GEPI_STORE; g.out = out_dev; g.ldo = N;
+		rc = launch_gemm(g, na, s);
+	}
+	cudaError_t e = cudaStreamSynchronize(s);
+	ah.release(); al.release(); bt.release();
+	if (rc != XALM_OK) return rc;
+	if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "gemm failed: %s", cudaGetErrorString(e));
+	return XALM_OK;
+}
+
+int prefill_bench_gemm(int T, int N, int K, int split, int iters, float* ms_per_launch) {
+	const int na = split == 2 ? 2 : 1;
+	const int MT = cdiv(T, GB_M), KT = cdiv(K, GB_K), NT = cdiv(N, GB_N);
+	cudaStream_t s;
+	XALM_CUDA_CHECK(cudaStreamCreate(&s));
+	DevBuf ah, al, bt, out;
+	XALM_TRY(ah.ensure((size_t) MT * KT * A_TILE_BYTES, true, s));
+	if (na == 2) XALM_TRY(al.ensure((size_t) MT * KT * A_TILE_BYTES, true, s));
+	XALM_TRY(bt.ensure((size_t) NT * KT * B_TILE_BYTES, true, s));
+	XALM_TRY(out.ensure((size_t) MT * GB_M * N * 4, true, s));
+	// fill the operands with a pattern of small finite fp16 values (0x2C00 = 0.0625)
+	XALM_CUDA_CHECK(cudaMemsetAsync(ah.p, 0x2C, (size_t) MT * KT * A_TILE_BYTES, s));
+	XALM_CUDA_CHECK(cudaMemsetAsync(bt.p, 0x2C, (size_t) NT * KT * B_TILE_BYTES, s));
+	GemmArgs g = {};
+	g.a_hi = ah.p; g.a_lo = al.p; g.b = bt.p;
+	g.MT = MT; g.NT = NT; g.KT = KT; g.M = T; g.N = N; g.epi = GEPI_STORE; g.out = reinterpret_cast<float*>(out.p); g.ldo = N;
+	cudaEvent_t e0, e1;
+	XALM_CUDA_CHECK(cudaEventCreate(&e0));
+	XALM_CUDA_CHECK(cudaEventCreate(&e1));
+	for (int i = 0; i < 3; i++) XALM_TRY(launch_gemm(g, na, s));
+	XALM_CUDA_CHECK(cudaEventRecord(e0, s));
+	for (int i = 0; i < iters; i++) XALM_TRY(launch_gemm(g, na, s));
+	XALM_CUDA_CHECK(cudaEventRecord(e1, s));
+	XALM_CUDA_CHECK(cudaStreamSynchronize(s));
+	float ms = 0.f;
+	XALM_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+	*ms_per_launch = ms / (float) iters;
+	cudaEventDestroy(e0); cudaEventDestroy(e1);
+	ah.release(); al.release(); bt.release(); out.release();
+	cudaStreamDestroy(s);
+	return XALM_OK;
+}
+
+} // namespace xalm

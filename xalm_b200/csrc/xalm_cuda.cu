@@ -28,6 +28,7 @@
 #include "matvec_tma.cuh"
 #include "megakernel.cuh"
 #include "prefetch.cuh"
+#include "prefill.h"
 
 namespace xalm {
 
@@ -66,6 +67,7 @@ static std::map<std::string, int>& tuning() {
 	    {"tma_rc", 0},       // 0 = auto, else force rows per tile (4 or 8)
 	    {"tma_ns_max", 4},   // most ring stages
 	    {"tma_ctas_per_sm", 2},
+	    {"prefill_split", 1}, // batched prefill: 1 = fp16 activations, 2 = hi+lo fp16 pair (two MMAs per weight tile)
 	};
 	return t;
 }
@@ -680,6 +682,9 @@ struct xalm_cuda_model {
 	MkArgs mk_args = {};
 	size_t mk_smem = 0;
 	int mk_type = 0;
+	// batched prefill (prefill.cu)
+	PrefillScratch* prefill = nullptr;
+	int last_prefill_launches = 0;
 };
 
 static int parse_tensor_name(const char* name, int n_layers, int* layer, int* piece) {
@@ -769,6 +774,9 @@ int xalm_cuda_create(const xalm_config* cfg, int device, int tp_rank, int tp_siz
 
 void xalm_cuda_destroy(xalm_cuda_model* m) {
 	if (!m) return;
+	cudaSetDevice(m->device);
+	prefill_free(m->prefill);
+	m->prefill = nullptr;
 	cudaSetDevice(m->device);
 	cudaStreamSynchronize(m->stream);
 	for (int i = 0; i < 2; i++)
@@ -1616,6 +1624,76 @@ int xalm_cuda_ffn(float* xout, const float* x, const void* w1, const void* w2, c
 	XALM_TRY(launch_matvec(b, 0, false));
 	XALM_CUDA_CHECK(cudaMemcpy(xout, dout, (size_t) dim * sizeof(float), cudaMemcpyDeviceToHost));
 	return XALM_OK;
+}
+
+static void fill_prefill_model(xalm_cuda_model* m, PrefillModel& pm) {
+	pm.c = m->c;
+	pm.q_dim = m->q_dim; pm.kv_dim = m->kv_dim;
+	pm.embed_raw = m->embed_raw; pm.embed_type = m->embed_type; pm.embed_row_bytes = m->embed_row_bytes;
+	pm.wcls = m->wcls.m; pm.rms_final = m->rms_final; pm.rms_final_type = m->rms_final_type;
+	pm.rope_freq = m->rope_freq;
+	pm.stream = m->stream;
+	pm.layers.resize(m->layers.size());
+	for (size_t l = 0; l < m->layers.size(); l++) {
+		LayerDev& L = m->layers[l];
+		PrefillLayer& P = pm.layers[l];
+		P.wqkv = L.wqkv.m; P.wo = L.wo.m; P.w13 = L.w13.m; P.w2 = L.w2.m; P.glu_off = m->hidden_l;
+		P.rms_att = L.rms_att; P.rms_ffn = L.rms_ffn; P.rms_att_type = L.rms_att_type; P.rms_ffn_type = L.rms_ffn_type;
+		P.k_cache = L.k_cache; P.v_cache = L.v_cache;
+	}
+}
+
+// ---- batched prefill / perplexity on the tensor-core path (prefill.cu) ----------------------------------------------------
+int xalm_cuda_prefill(xalm_cuda_model* m, const int* tokens, int n, int pos0, int want_logits, float* logits_host, const int* targets,
+                      float* probs_host) {
+	if (!m || !tokens) return set_error(XALM_ERR_INVALID, "NULL argument");
+	if (!m->finalized) return set_error(XALM_ERR_STATE, "prefill before finalize");
+	if (m->tp_size > 1) return set_error(XALM_ERR_UNSUPPORTED, "prefill: tensor-parallel models take the token-at-a-time path");
+	if (want_logits < 0 || want_logits > 2) return set_error(XALM_ERR_INVALID, "prefill: want_logits = %d", want_logits);
+	XALM_CUDA_CHECK(cudaSetDevice(m->device));
+	PrefillModel pm;
+	fill_prefill_model(m, pm);
+	const int split = tune("prefill_split");
+	XALM_TRY(prefill_run(pm, &m->prefill, tokens, n, pos0, want_logits, logits_host, targets, probs_host, split, &m->last_prefill_launches));
+	cudaError_t e = cudaStreamSynchronize(m->stream);
+	if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "prefill failed: %s", cudaGetErrorString(e));
+	m->last_launches = m->last_prefill_launches;
+	return XALM_OK;
+}
+
+int xalm_cuda_prefill_async(xalm_cuda_model* m, const int* tokens, int n, int pos0, int want_logits) {
+	if (!m || !tokens) return set_error(XALM_ERR_INVALID, "NULL argument");
+	// same as xalm_cuda_prefill without the host synchronisation and read-back (bench.py's device-timed leg)
+	if (!m->finalized) return set_error(XALM_ERR_STATE, "prefill before finalize");
+	if (m->tp_size > 1) return set_error(XALM_ERR_UNSUPPORTED, "prefill: tensor-parallel models take the token-at-a-time path");
+	XALM_CUDA_CHECK(cudaSetDevice(m->device));
+	PrefillModel pm;
+	fill_prefill_model(m, pm);
+	XALM_TRY(prefill_run(pm, &m->prefill, tokens, n, pos0, want_logits, nullptr, nullptr, nullptr, tune("prefill_split"), &m->last_prefill_launches));
+	m->last_launches = m->last_prefill_launches;
+	return XALM_OK;
+}
+
+// out(T,N) = a(T,K) . W(N,K)^T — the batched form of matmul (model.h:315) on the tcgen05 path, host pointers in and out
+int xalm_cuda_gemm(float* out, const float* a, const void* w, int type_id, int T, int K, int N, int split) {
+	if (!out || !a || !w) return set_error(XALM_ERR_INVALID, "NULL argument");
+	if (T <= 0 || K <= 0 || N <= 0 || K % 32 || N % 32) return set_error(XALM_ERR_INVALID, "gemm: T=%d K=%d N=%d (K, N positive multiples of 32)", T, K, N);
+	XALM_TRY(need_device());
+	TmpDev t;
+	WMat wm;
+	XALM_TRY(tmp_weight(t, wm, type_id, w, N, K));
+	void *da, *dout;
+	XALM_TRY(t.put(&da, a, (size_t) T * K * sizeof(float)));
+	XALM_TRY(t.alloc(&dout, (size_t) T * N * sizeof(float)));
+	XALM_TRY(prefill_gemm_dev(wm, (const float*) da, T, (float*) dout, split, 0));
+	XALM_CUDA_CHECK(cudaMemcpy(out, dout, (size_t) T * N * sizeof(float), cudaMemcpyDeviceToHost));
+	return XALM_OK;
+}
+
+int xalm_cuda_bench_gemm(int T, int N, int K, int split, int iters, float* ms_per_launch) {
+	if (!ms_per_launch || T <= 0 || N <= 0 || K <= 0 || iters <= 0) return set_error(XALM_ERR_INVALID, "bench_gemm: bad argument");
+	XALM_TRY(need_device());
+	return prefill_bench_gemm(T, N, K, split, iters, ms_per_launch);
 }
 
 int xalm_cuda_timeline(int n_records, unsigned long long* out, int* n_out) {

@@ -149,6 +149,28 @@ class Model:
     def sync(self):
         capi.check(capi.lib().xalm_cuda_sync(self._h))
 
+    # ---- batched prefill: the per-position loops of main.cpp:94-100 / :244-254 in one pass (tcgen05 GEMMs) ----
+    def prefill(self, tokens, pos0: int = 0, want_logits: int = 1, targets=None):
+        """Positions pos0..pos0+len(tokens)-1 at once.  want_logits 0: hydrate only -> None; 1: logits of the last
+        position (vocab,); 2: all positions (n, vocab).  With `targets` returns (logits, probs) where probs[i] is
+        Sampler.sample_prob(targets[i]) at position pos0+i."""
+        if self._h is None:
+            raise RuntimeError("Model.prefill: the model is not on a CUDA device (call model.cuda()); this backend has no CPU path")
+        tok = np.ascontiguousarray(tokens, dtype=np.int32)
+        n = int(tok.size)
+        V = self.config["vocab_size"]
+        lg = None if want_logits == 0 else np.empty(V if want_logits == 1 else (n, V), dtype=np.float32)
+        tg = pr = None
+        if targets is not None:
+            tg = np.ascontiguousarray(targets, dtype=np.int32)
+            pr = np.empty(n, dtype=np.float32)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+        capi.check(capi.lib().xalm_cuda_prefill(self._h, vp(tok), n, pos0, want_logits, vp(lg), vp(tg), vp(pr)))
+        return (lg, pr) if targets is not None else lg
+
+    def prefill_async(self, tokens: np.ndarray, pos0: int = 0, want_logits: int = 2) -> None:
+        capi.check(capi.lib().xalm_cuda_prefill_async(self._h, tokens.ctypes.data_as(C.c_void_p), int(tokens.size), pos0, want_logits))
+
     def active_bytes(self, pos: int) -> int:
         """Model::active_bytes (model.cpp:12-35) for THIS rank's shard, from the device-side tensor types."""
         b = C.c_longlong(0)
