@@ -75,7 +75,6 @@ def test_prefill_logits_match_oracle(wtype, shape, n, split):
         got = gm.prefill(tokens, 0, want_logits=2)
         diff = float(np.max(np.abs(got - ref)))
         assert diff <= LOGIT_TOL, f"{wtype}/{shape}: prefill logits differ from the oracle by {diff}"
-        assert np.array_equal(np.argmax(got, axis=1), np.argmax(ref, axis=1)) or diff < 1e-3
         # the KV cache the prefill leaves behind is the one the token loop would have written (fp16-operand rounding aside)
         for layer in range(config["n_layers"]):
             for which in (0, 1):
