@@ -25,7 +25,7 @@ def _fp16(x):
 
 
 @pytest.mark.parametrize("wtype", ALL)
-@pytest.mark.parametrize("split", [1, 2])
+@pytest.mark.parametrize("split", [1, 2, 3])
 def test_gemm_every_format(wtype, split):
     t = T.parse(wtype)
     Tn, K, N = 150, 512, 320           # ragged: T not a multiple of 128, N not a multiple of 256; K = 2 units (TMA layout) for block formats
@@ -33,6 +33,10 @@ def test_gemm_every_format(wtype, split):
     w = capi.dequant(t.id, raw, N * K).reshape(N, K)
     a = synth.normal(5, 77, Tn * K, 1.0).reshape(Tn, K)
     out = capi.gemm(a, raw, t.id, K, N, split)
+    if split == 3:   # hi+lo on both operands: fp32-grade products (what is dropped: lo x lo ~ 2^-22 and the lo planes' own rounding)
+        exact = a.astype(np.float64) @ w.astype(np.float64).T
+        assert np.max(np.abs(out - exact)) <= 3e-6 * float(np.abs(exact).max()) + 1e-7, f"{wtype}: {np.max(np.abs(out - exact))}"
+        return
     wh = _fp16(w).astype(np.float64)
     if split == 1:
         ref = _fp16(a).astype(np.float64) @ wh.T
@@ -64,7 +68,7 @@ def _oracle_all_logits(om, tokens):
 
 @pytest.mark.parametrize("wtype,shape,n", [("f16", "tiny", 100), ("q8_0", "tiny", 128), ("q4_0", "tiny", 37), ("q5_1", "tiny", 70),
                                            ("q8_0", "small", 200), ("f16", "small", 130)])
-@pytest.mark.parametrize("split", [1, 2])
+@pytest.mark.parametrize("split", [1, 2, 3])
 def test_prefill_logits_match_oracle(wtype, shape, n, split):
     capi.tune("prefill_split", split)
     try:
@@ -74,7 +78,7 @@ def test_prefill_logits_match_oracle(wtype, shape, n, split):
         ref = _oracle_all_logits(om, tokens)
         got = gm.prefill(tokens, 0, want_logits=2)
         diff = float(np.max(np.abs(got - ref)))
-        assert diff <= LOGIT_TOL, f"{wtype}/{shape}: prefill logits differ from the oracle by {diff}"
+        assert diff <= (LOGIT_TOL if split < 3 else 1e-3), f"{wtype}/{shape}: prefill logits differ from the oracle by {diff}"
         # the KV cache the prefill leaves behind is the one the token loop would have written (fp16-operand rounding aside)
         for layer in range(config["n_layers"]):
             for which in (0, 1):

@@ -176,7 +176,8 @@ __device__ inline void wmat_decode8(const WMat& w, int r, int k0, float (&v)[8])
 // One thread per 16-byte chunk of the destination, in destination order (coalesced stores).  Destination row n of
 // B tile `nt`: plain matrices -> physical row nt*256 + n;  GLU (glu_off > 0 or glu) -> n < 128: W1 row nt*128 + n,
 // else W3 row glu_off + nt*128 + (n-128), so gate and up of the same hidden unit land in one accumulator row block.
-__global__ void dequant_tiles_kernel(const WMat w, int glu, int glu_off, int n_valid, int K, int NT, int KT, uint8_t* __restrict__ dst) {
+__global__ void dequant_tiles_kernel(const WMat w, int glu, int glu_off, int n_valid, int K, int NT, int KT, uint8_t* __restrict__ dst,
+                                     uint8_t* __restrict__ dst_lo) {
 	const size_t chunks_per_tile = B_TILE_BYTES / 16;
 	const size_t total = (size_t) NT * KT * chunks_per_tile;
 	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
@@ -196,16 +197,22 @@ __global__ void dequant_tiles_kernel(const WMat w, int glu, int glu_off, int n_v
 			prow = nt * GB_N + r;
 			valid = prow < n_valid;
 		}
-		uint4 out = make_uint4(0, 0, 0, 0);
+		uint4 out = make_uint4(0, 0, 0, 0), out_lo = make_uint4(0, 0, 0, 0);
 		if (valid && k0 < K) {
 			float v[8];
 			wmat_decode8(w, prow, k0, v);
-			__half2 h[4];
+			__half2 h[4], l[4];
 #pragma unroll
-			for (int j = 0; j < 4; j++) h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+			for (int j = 0; j < 4; j++) {
+				h[j] = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+				const float2 f = __half22float2(h[j]);
+				l[j] = __floats2half2_rn(v[2 * j] - f.x, v[2 * j + 1] - f.y); // what fp16 dropped (exact difference, then rounded)
+			}
 			out = *reinterpret_cast<const uint4*>(h);
+			out_lo = *reinterpret_cast<const uint4*>(l);
 		}
 		*reinterpret_cast<uint4*>(dst + i * 16) = out;
+		if (dst_lo) *reinterpret_cast<uint4*>(dst_lo + i * 16) = out_lo;
 	}
 }
 
@@ -286,6 +293,21 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
 	for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+	uint32_t r[32];
+	__syncwarp();
+	asm volatile(
+	    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+	    "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+	    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+	      "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+	      "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+	      "=r"(r[30]), "=r"(r[31])
+	    : "r"(taddr));
+	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+	for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 	uint32_t r[8];
 	__syncwarp();
@@ -310,6 +332,7 @@ struct GemmArgs {
 	const uint8_t* a_hi;
 	const uint8_t* a_lo;
 	const uint8_t* b;
+	const uint8_t* b_lo; // residual plane of the weights (NB = 2)
 	int MT, NT, KT;     // tile counts; M tiles are [mt0, mt0 + MT)
 	int mt0;
 	int M;              // valid rows
@@ -320,9 +343,10 @@ struct GemmArgs {
 	int out_row0;
 	// QKV
 	__half* q_out;      // (T, q_dim) row-major fp16, RoPE applied
+	__half* q_lo;       // fp16 of what q_out's rounding dropped (precise mode), or nullptr
 	__half* k_cache;
 	__half* v_cache;
-	const float* rope_freq;
+	const float2* rope_cs; // (T, head_dim/2): {cos, sin}(pos * freq) per row, from rope_table_kernel
 	int q_dim, kv_dim, head_dim, pos0;
 	float qkv_clip;
 	// GLU
@@ -331,16 +355,18 @@ struct GemmArgs {
 };
 
 constexpr int GEMM_THREADS = 192;
-template <int NA>
+// NA activation planes x NB weight planes: (1,1) fp16 x fp16; (2,1) hi+lo activations; (2,2) hi+lo on both sides, three MMAs per
+// K step (hi.hi + lo.hi + hi.lo; lo.lo is below fp32 resolution) = fp32-grade products on the fp16 tensor pipe
+template <int NA, int NB>
 struct GemmCfg {
-	static constexpr int STAGE = NA * A_TILE_BYTES + B_TILE_BYTES;
-	static constexpr int NS = NA == 1 ? 4 : 3;
+	static constexpr int STAGE = NA * A_TILE_BYTES + NB * B_TILE_BYTES;
+	static constexpr int NS = (200 * 1024) / STAGE;
 	static constexpr size_t SMEM = (size_t) NS * STAGE + 1024 /* alignment slack */ + 256 /* barriers */;
 };
 
-template <int NA>
+template <int NA, int NB>
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmArgs g) {
-	using Cfg = GemmCfg<NA>;
+	using Cfg = GemmCfg<NA, NB>;
 	constexpr int NS = Cfg::NS;
 	extern __shared__ uint8_t smem_raw[];
 	// 1024-byte alignment in the SHARED address space (the swizzle pattern is a function of the address bits)
@@ -381,6 +407,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmArgs
 				const uint8_t* ah = g.a_hi + (size_t) mt * KT * A_TILE_BYTES;
 				const uint8_t* al = NA == 2 ? g.a_lo + (size_t) mt * KT * A_TILE_BYTES : nullptr;
 				const uint8_t* bt = g.b + (size_t) nt * KT * B_TILE_BYTES;
+				const uint8_t* bl = NB == 2 ? g.b_lo + (size_t) nt * KT * B_TILE_BYTES : nullptr;
 				for (int kt = 0; kt < KT; kt++) {
 					mb_wait(&empty[slot], phase ^ 1);
 					uint8_t* st = smem + (size_t) slot * Cfg::STAGE;
@@ -388,6 +415,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmArgs
 					bulk_load(st, ah + (size_t) kt * A_TILE_BYTES, A_TILE_BYTES, &full[slot]);
 					if (NA == 2) bulk_load(st + A_TILE_BYTES, al + (size_t) kt * A_TILE_BYTES, A_TILE_BYTES, &full[slot]);
 					bulk_load(st + NA * A_TILE_BYTES, bt + (size_t) kt * B_TILE_BYTES, B_TILE_BYTES, &full[slot]);
+					if (NB == 2) bulk_load(st + NA * A_TILE_BYTES + B_TILE_BYTES, bl + (size_t) kt * B_TILE_BYTES, B_TILE_BYTES, &full[slot]);
 					if (++slot == NS) { slot = 0; phase ^= 1; }
 				}
 			}
@@ -405,10 +433,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmArgs
 					mb_wait(&full[slot], phase);
 					tc_fence_after();
 					const uint32_t sa = s_u32(smem + (size_t) slot * Cfg::STAGE);
-					const uint64_t bdesc = smem_desc(sa + NA * A_TILE_BYTES);
 #pragma unroll
-					for (int p = 0; p < NA; p++) {
-						const uint64_t adesc = smem_desc(sa + p * A_TILE_BYTES);
+					for (int p = 0; p < NA + NB - 1; p++) { // (a_hi, b_hi), (a_lo, b_hi), (a_hi, b_lo)
+						const uint64_t adesc = smem_desc(sa + (p == 1 ? A_TILE_BYTES : 0));
+						const uint64_t bdesc = smem_desc(sa + NA * A_TILE_BYTES + (p == 2 ? B_TILE_BYTES : 0));
 #pragma unroll
 						for (int k = 0; k < GB_K / UMMA_K; k++) {
 							// advancing K by 16 fp16 = 32 bytes inside the 128-byte swizzle row: +2 in the (>>4) address field
@@ -447,43 +475,56 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmArgs
 						store_a8(g.o, m, o0, h);
 					}
 				}
-			} else {
+			} else if (g.epi == GEPI_QKV) {
+				const int pos = g.pos0 + m;
+				const float2* cs_row = g.rope_cs + (size_t) (mrow ? m : 0) * (g.head_dim / 2);
 				for (int c = 0; c < GB_N; c += 16) {
 					float v[16];
 					tmem_ld16(taddr + c, v);
 					const int n0 = nt * GB_N + c;
 					if (!mrow || n0 >= g.N) continue;
-					if (g.epi == GEPI_QKV) {
-						const int pos = g.pos0 + m;
 #pragma unroll
-						for (int i = 0; i < 16; i += 2) {
-							const int n = n0 + i;
-							if (n >= g.N) break;
-							float v0 = clipf(v[i], g.qkv_clip), v1 = clipf(v[i + 1], g.qkv_clip); // infer.cpp:389-399
-							if (n < g.q_dim) {
-								rope_pair(v0, v1, n % g.head_dim, pos, g.rope_freq);
-								*reinterpret_cast<__half2*>(g.q_out + (size_t) m * g.q_dim + n) = __floats2half2_rn(v0, v1);
-							} else if (n < g.q_dim + g.kv_dim) {
-								const int j = n - g.q_dim;
-								rope_pair(v0, v1, j % g.head_dim, pos, g.rope_freq);
-								*reinterpret_cast<__half2*>(g.k_cache + (size_t) pos * g.kv_dim + j) = __floats2half2_rn(v0, v1);
-							} else {
-								const int j = n - g.q_dim - g.kv_dim;
-								*reinterpret_cast<__half2*>(g.v_cache + (size_t) pos * g.kv_dim + j) = __floats2half2_rn(v0, v1);
-							}
+					for (int i = 0; i < 16; i += 2) {
+						const int n = n0 + i;
+						if (n >= g.N) break;
+						float v0 = clipf(v[i], g.qkv_clip), v1 = clipf(v[i + 1], g.qkv_clip); // infer.cpp:389-399
+						if (n < g.q_dim + g.kv_dim) { // rope (infer.cpp:305-322) on q and k: same sincosf(pos * freq) values as the decode kernels
+							const int j = (n < g.q_dim ? n : n - g.q_dim) % g.head_dim;
+							const float2 cs = cs_row[j >> 1];
+							const float a0 = v0, b0 = v1;
+							v0 = a0 * cs.x - b0 * cs.y;
+							v1 = a0 * cs.y + b0 * cs.x;
 						}
-					} else {
-						float* o = g.out + (size_t) (m - g.out_row0) * g.ldo + n0;
+						const __half2 h = __floats2half2_rn(v0, v1);
+						if (n < g.q_dim) {
+							*reinterpret_cast<__half2*>(g.q_out + (size_t) m * g.q_dim + n) = h;
+							if (g.q_lo) {
+								const float2 f = __half22float2(h);
+								*reinterpret_cast<__half2*>(g.q_lo + (size_t) m * g.q_dim + n) = __floats2half2_rn(v0 - f.x, v1 - f.y);
+							}
+						} else if (n < g.q_dim + g.kv_dim) {
+							*reinterpret_cast<__half2*>(g.k_cache + (size_t) pos * g.kv_dim + (n - g.q_dim)) = h;
+						} else {
+							*reinterpret_cast<__half2*>(g.v_cache + (size_t) pos * g.kv_dim + (n - g.q_dim - g.kv_dim)) = h;
+						}
+					}
+				}
+			} else {
+				for (int c = 0; c < GB_N; c += 32) { // 32 columns = one full 128-byte line per thread
+					float v[32];
+					tmem_ld32(taddr + c, v);
+					const int n0 = nt * GB_N + c;
+					if (!mrow || n0 >= g.N) continue;
+					float* o = g.out + (size_t) (m - g.out_row0) * g.ldo + n0;
 #pragma unroll
-						for (int i = 0; i < 16; i += 4) {
-							if (n0 + i >= g.N) break;
-							float4 r = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-							if (g.epi == GEPI_RESID) {
-								const float4 x = *reinterpret_cast<const float4*>(o + i);
-								r.x += x.x; r.y += x.y; r.z += x.z; r.w += x.w; // infer.cpp:450-452, :492-494
-							}
-							*reinterpret_cast<float4*>(o + i) = r;
+					for (int i = 0; i < 32; i += 4) {
+						if (n0 + i >= g.N) break;
+						float4 r = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+						if (g.epi == GEPI_RESID) {
+							const float4 x = *reinterpret_cast<const float4*>(o + i);
+							r.x += x.x; r.y += x.y; r.z += x.z; r.w += x.w; // infer.cpp:450-452, :492-494
 						}
+						*reinterpret_cast<float4*>(o + i) = r;
 					}
 				}
 			}
@@ -515,29 +556,68 @@ __global__ void embed_rows_kernel(int type, const uint8_t* __restrict__ table, s
 	}
 }
 
-// rmsnorm (infer.cpp:224-236) of each row, result as an A-tile operand.  One warp per row.
+// {cos, sin}(pos * freq_j) for every row and rotation pair: the very expression rope_pair (matvec.cuh) evaluates per token
+__global__ void rope_table_kernel(const float* __restrict__ freq, int half_dim, int T, int pos0, float2* __restrict__ cs) {
+	const int total = T * half_dim;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+		const int m = i / half_dim, j = i % half_dim;
+		const float val = (float) (pos0 + m) * freq[j];
+		float sn, cn;
+		sincosf(val, &sn, &cn);
+		cs[i] = make_float2(cn, sn);
+	}
+}
+
+// rmsnorm (infer.cpp:224-236) of each row, result as an A-tile operand.  One warp per row, the row held in registers.
 __global__ void rmsnorm_rows_kernel(const float* __restrict__ x, int T, int dim, const uint8_t* __restrict__ w, int wtype, float eps, ATiles o) {
 	const int warps = blockDim.x >> 5;
 	const int lane = threadIdx.x & 31;
+	constexpr int MAXC = 16; // 8-element chunks per lane kept in registers (rows up to 4096 elements); longer rows re-read the tail
 	for (int m = blockIdx.x * warps + (threadIdx.x >> 5); m < T; m += gridDim.x * warps) {
 		const float* xr = x + (size_t) m * dim;
+		float4 buf[MAXC][2];
 		float ss = 0.f;
-		for (int j = lane * 4; j < dim; j += 128) {
-			const float4 v = *reinterpret_cast<const float4*>(xr + j);
-			ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+#pragma unroll
+		for (int c = 0; c < MAXC; c++) {
+			const int j = lane * 8 + c * 256;
+			if (j < dim) {
+				buf[c][0] = *reinterpret_cast<const float4*>(xr + j);
+				buf[c][1] = *reinterpret_cast<const float4*>(xr + j + 4);
+				const float4 a = buf[c][0], b = buf[c][1];
+				ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
+			}
+		}
+		for (int j = lane * 8 + MAXC * 256; j < dim; j += 256) {
+			const float4 a = *reinterpret_cast<const float4*>(xr + j), b = *reinterpret_cast<const float4*>(xr + j + 4);
+			ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
 		}
 		ss = warp_sum(ss);
 		const float scale = 1.0f / sqrtf(ss / (float) dim + eps);
-		for (int j = lane * 8; j < dim; j += 256) {
+		auto emit = [&](int j, const float4& a, const float4& b) {
+			const float xv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+			float gw[8];
+			if (wtype == XALM_F32) {
+				const float4 g0 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(w) + j);
+				const float4 g1 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(w) + j + 4);
+				gw[0] = g0.x; gw[1] = g0.y; gw[2] = g0.z; gw[3] = g0.w; gw[4] = g1.x; gw[5] = g1.y; gw[6] = g1.z; gw[7] = g1.w;
+			} else {
+				const uint4 gq = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(w) + j);
+				const uint32_t u[4] = {gq.x, gq.y, gq.z, gq.w};
+#pragma unroll
+				for (int i = 0; i < 4; i++) { gw[2 * i] = __uint_as_float(u[i] << 16); gw[2 * i + 1] = __uint_as_float(u[i] & 0xFFFF0000u); }
+			}
 			float v[8];
 #pragma unroll
-			for (int i = 0; i < 8; i++) {
-				const float gw = wtype == XALM_F32 ? reinterpret_cast<const float*>(w)[j + i]
-				                                   : bf16_bits_to_f32(reinterpret_cast<const uint16_t*>(w)[j + i]);
-				v[i] = xr[j + i] * scale * gw; // infer.cpp:233-235
-			}
+			for (int i = 0; i < 8; i++) v[i] = xv[i] * scale * gw[i]; // infer.cpp:233-235
 			store_a8(o, m, j, v);
+		};
+#pragma unroll
+		for (int c = 0; c < MAXC; c++) {
+			const int j = lane * 8 + c * 256;
+			if (j < dim) emit(j, buf[c][0], buf[c][1]);
 		}
+		for (int j = lane * 8 + MAXC * 256; j < dim; j += 256)
+			emit(j, *reinterpret_cast<const float4*>(xr + j), *reinterpret_cast<const float4*>(xr + j + 4));
 	}
 }
 
@@ -574,6 +654,7 @@ __global__ void target_prob_kernel(const float* __restrict__ logits, int vocab, 
 // ------------------------------------------------------------------------------------------------------------------
 struct AttnPArgs {
 	const __half* q;       // (T, q_dim)
+	const __half* q_lo;    // rounding residual of q (PRECISE), or nullptr
 	const __half* k_cache; // (max_seq_len, kv_dim)
 	const __half* v_cache;
 	ATiles o;              // xb2
@@ -600,14 +681,16 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 	return *reinterpret_cast<const uint32_t*>(&h);
 }
 
-template <int HD>
+// PRECISE: q and the softmax probabilities enter the tensor cores as hi+lo fp16 pairs (two MMAs each) — with the split GEMMs
+// this keeps the whole prefill at fp32-grade operand precision (K and V are fp16 in the reference too).
+template <int HD, bool PRECISE>
 __global__ void __launch_bounds__(128) attn_prefill_kernel(const AttnPArgs a) {
 	constexpr int BQ = 64, BKV = 64;
 	constexpr int CPR = HD / 8;         // 16-byte chunks per row
 	constexpr int ROWB = HD * 2;        // bytes per row
 	extern __shared__ __align__(128) uint8_t sm[];
-	uint8_t* sQ = sm;
-	uint8_t* sK = sQ + BQ * ROWB;       // [2][BKV][HD]
+	uint8_t* sQ = sm;                   // [1 or 2][BQ][HD]
+	uint8_t* sK = sQ + (PRECISE ? 2 : 1) * BQ * ROWB; // [2][BKV][HD]
 	uint8_t* sV = sK + 2 * BKV * ROWB;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int qt = a.n_qt - 1 - (int) blockIdx.x; // longest (latest) query tiles first
@@ -625,6 +708,7 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(const AttnPArgs a) {
 		const int r = i / CPR, c = i % CPR;
 		const bool ok = q0 + r < a.T;
 		cp_async16(s_u32(sQ) + soff(r, c), a.q + (size_t) (ok ? q0 + r : 0) * a.q_dim + h * HD + c * 8, ok);
+		if (PRECISE) cp_async16(s_u32(sQ) + BQ * ROWB + soff(r, c), a.q_lo + (size_t) (ok ? q0 + r : 0) * a.q_dim + h * HD + c * 8, ok);
 	}
 	auto load_kv = [&](int kb, int buf) {
 		for (int i = threadIdx.x; i < BKV * CPR; i += 128) {
@@ -646,6 +730,7 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(const AttnPArgs a) {
 		for (int j = 0; j < 4; j++) o_acc[i][j] = 0.f;
 	float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
 	uint32_t qf[HD / 16][4];
+	uint32_t qlf[PRECISE ? HD / 16 : 1][4];
 	const float scale = 1.0f / sqrtf((float) HD);
 	const int row_a = q0 + warp * 16 + (lane >> 2); // this thread's two query rows: row_a and row_a + 8
 	bool q_loaded = false;
@@ -658,7 +743,10 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(const AttnPArgs a) {
 		__syncthreads();
 		if (!q_loaded) {
 #pragma unroll
-			for (int ks = 0; ks < HD / 16; ks++) ldsm4(qf[ks], s_u32(sQ) + soff(warp * 16 + (lane & 15), ks * 2 + (lane >> 4)));
+			for (int ks = 0; ks < HD / 16; ks++) {
+				ldsm4(qf[ks], s_u32(sQ) + soff(warp * 16 + (lane & 15), ks * 2 + (lane >> 4)));
+				if (PRECISE) ldsm4(qlf[ks], s_u32(sQ) + BQ * ROWB + soff(warp * 16 + (lane & 15), ks * 2 + (lane >> 4)));
+			}
 			q_loaded = true;
 		}
 		// ---- S = Q K^T (16 query rows x 64 keys per warp) ----
@@ -676,6 +764,10 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(const AttnPArgs a) {
 				ldsm4(kf, kbase + soff(nb * 16 + (lane & 7) + ((lane >> 4) << 3), ks * 2 + ((lane >> 3) & 1)));
 				mma16816(s[2 * nb], qf[ks], kf[0], kf[1]);
 				mma16816(s[2 * nb + 1], qf[ks], kf[2], kf[3]);
+				if (PRECISE) {
+					mma16816(s[2 * nb], qlf[ks], kf[0], kf[1]);
+					mma16816(s[2 * nb + 1], qlf[ks], kf[2], kf[3]);
+				}
 			}
 		}
 		// ---- scale, causal mask, online softmax ----
@@ -725,17 +817,27 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(const AttnPArgs a) {
 		const uint32_t vbase = s_u32(sV) + buf * BKV * ROWB;
 #pragma unroll
 		for (int kk = 0; kk < BKV / 16; kk++) {
-			uint32_t pf[4];
-			pf[0] = pack_h2(s[2 * kk][0], s[2 * kk][1]);
-			pf[1] = pack_h2(s[2 * kk][2], s[2 * kk][3]);
-			pf[2] = pack_h2(s[2 * kk + 1][0], s[2 * kk + 1][1]);
-			pf[3] = pack_h2(s[2 * kk + 1][2], s[2 * kk + 1][3]);
+			uint32_t pf[4], pl[4];
+#pragma unroll
+			for (int f = 0; f < 4; f++) {
+				const float p0 = s[2 * kk + (f >> 1)][2 * (f & 1)], p1 = s[2 * kk + (f >> 1)][2 * (f & 1) + 1];
+				const __half2 hh = __floats2half2_rn(p0, p1);
+				pf[f] = *reinterpret_cast<const uint32_t*>(&hh);
+				if (PRECISE) {
+					const float2 back = __half22float2(hh);
+					pl[f] = pack_h2(p0 - back.x, p1 - back.y);
+				}
+			}
 #pragma unroll
 			for (int nb = 0; nb < HD / 16; nb++) {
 				uint32_t vf[4];
 				ldsm4_t(vf, vbase + soff(kk * 16 + (lane & 7) + (((lane >> 3) & 1) << 3), nb * 2 + (lane >> 4)));
 				mma16816(o_acc[2 * nb], pf, vf[0], vf[1]);
 				mma16816(o_acc[2 * nb + 1], pf, vf[2], vf[3]);
+				if (PRECISE) {
+					mma16816(o_acc[2 * nb], pl, vf[0], vf[1]);
+					mma16816(o_acc[2 * nb + 1], pl, vf[2], vf[3]);
+				}
 			}
 		}
 		__syncthreads(); // everyone is done with `buf` before the next iteration's prefetch overwrites it
@@ -815,16 +917,23 @@ struct DevBuf {
 };
 
 struct PrefillScratch {
-	DevBuf x, xb_hi, xb_lo, xb2_hi, xb2_lo, hb_hi, hb_lo, q, wt, logits, tokens, targets, probs;
+	DevBuf x, xb_hi, xb_lo, xb2_hi, xb2_lo, hb_hi, hb_lo, q, q_lo, wt[2], wt_lo[2], logits, tokens, targets, probs, rope;
 	int logits_rows = 0;
-	int attn_smem_set = 0;
-	bool gemm_attr_set[3] = {false, false, false};
+	cudaStream_t side = nullptr;          // dequantises the NEXT GEMM's weights while the current GEMM runs
+	cudaEvent_t ev_start = nullptr, ev_deq[2] = {nullptr, nullptr}, ev_gemm[2] = {nullptr, nullptr};
 };
 
 void prefill_free(PrefillScratch* s) {
 	if (!s) return;
-	DevBuf* all[] = {&s->x, &s->xb_hi, &s->xb_lo, &s->xb2_hi, &s->xb2_lo, &s->hb_hi, &s->hb_lo, &s->q, &s->wt, &s->logits, &s->tokens, &s->targets, &s->probs};
+	DevBuf* all[] = {&s->x, &s->xb_hi, &s->xb_lo, &s->xb2_hi, &s->xb2_lo, &s->hb_hi, &s->hb_lo, &s->q, &s->q_lo, &s->wt[0], &s->wt[1],
+	                 &s->wt_lo[0], &s->wt_lo[1], &s->logits, &s->tokens, &s->targets, &s->probs, &s->rope};
 	for (DevBuf* b : all) b->release();
+	if (s->side) cudaStreamDestroy(s->side);
+	if (s->ev_start) cudaEventDestroy(s->ev_start);
+	for (int i = 0; i < 2; i++) {
+		if (s->ev_deq[i]) cudaEventDestroy(s->ev_deq[i]);
+		if (s->ev_gemm[i]) cudaEventDestroy(s->ev_gemm[i]);
+	}
 	delete s;
 }
 const float* prefill_logits_dev(const PrefillScratch* s, int* rows) {
@@ -832,35 +941,34 @@ const float* prefill_logits_dev(const PrefillScratch* s, int* rows) {
 	return s ? reinterpret_cast<const float*>(s->logits.p) : nullptr;
 }
 
-static bool g_gemm_attr[3] = {false, false, false};
-static int launch_gemm(const GemmArgs& g, int na, cudaStream_t s) {
+template <int NA, int NB>
+static int launch_gemm_inst(const GemmArgs& g, int grid, cudaStream_t s) {
+	static bool attr = false;
+	if (!attr) {
+		XALM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<NA, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) GemmCfg<NA, NB>::SMEM));
+		attr = true;
+	}
+	gemm_tc_kernel<NA, NB><<<grid, GEMM_THREADS, GemmCfg<NA, NB>::SMEM, s>>>(g);
+	return XALM_OK;
+}
+static int launch_gemm(const GemmArgs& g, int na, int nb, cudaStream_t s) {
 	const int tiles = g.MT * g.NT;
 	if (tiles <= 0) return XALM_OK;
 	const int grid = std::min(tiles, sm_count());
-	cudaError_t e;
-	if (na == 2) {
-		if (!g_gemm_attr[2]) {
-			XALM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) GemmCfg<2>::SMEM));
-			g_gemm_attr[2] = true;
-		}
-		gemm_tc_kernel<2><<<grid, GEMM_THREADS, GemmCfg<2>::SMEM, s>>>(g);
-	} else {
-		if (!g_gemm_attr[1]) {
-			XALM_CUDA_CHECK(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) GemmCfg<1>::SMEM));
-			g_gemm_attr[1] = true;
-		}
-		gemm_tc_kernel<1><<<grid, GEMM_THREADS, GemmCfg<1>::SMEM, s>>>(g);
-	}
-	e = cudaGetLastError();
+	if (na == 2 && nb == 2) XALM_TRY((launch_gemm_inst<2, 2>(g, grid, s)));
+	else if (na == 2) XALM_TRY((launch_gemm_inst<2, 1>(g, grid, s)));
+	else XALM_TRY((launch_gemm_inst<1, 1>(g, grid, s)));
+	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "gemm_tc launch failed: %s", cudaGetErrorString(e));
 	return XALM_OK;
 }
 
-// weights of `w` (rows [0, n_valid) or the GLU pairing) -> B tiles in `dst`
-static int launch_dequant_tiles(const WMat& w, bool glu, int glu_off, int n_valid, int K, int NT, int KT, uint8_t* dst, cudaStream_t s) {
+// weights of `w` (rows [0, n_valid) or the GLU pairing) -> B tiles in `dst` (+ rounding residuals in dst_lo when not NULL)
+static int launch_dequant_tiles(const WMat& w, bool glu, int glu_off, int n_valid, int K, int NT, int KT, uint8_t* dst, uint8_t* dst_lo,
+                                cudaStream_t s) {
 	const size_t chunks = (size_t) NT * KT * (B_TILE_BYTES / 16);
 	const int grid = (int) std::min<size_t>((chunks + 255) / 256, (size_t) sm_count() * 16);
-	dequant_tiles_kernel<<<grid, 256, 0, s>>>(w, glu ? 1 : 0, glu_off, n_valid, K, NT, KT, dst);
+	dequant_tiles_kernel<<<grid, 256, 0, s>>>(w, glu ? 1 : 0, glu_off, n_valid, K, NT, KT, dst, dst_lo);
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "dequant_tiles launch failed: %s", cudaGetErrorString(e));
 	return XALM_OK;
@@ -871,15 +979,15 @@ static bool prefill_type_ok(int t) {
 	return type_info(t, &ti);
 }
 
-template <int HD>
+template <int HD, bool PRECISE>
 static int launch_attn_p(const AttnPArgs& a, cudaStream_t s) {
-	const size_t smem = (size_t) 64 * HD * 2 * 5;
+	const size_t smem = (size_t) 64 * HD * 2 * (PRECISE ? 6 : 5);
 	static bool attr = false;
 	if (!attr) {
-		XALM_CUDA_CHECK(cudaFuncSetAttribute(attn_prefill_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+		XALM_CUDA_CHECK(cudaFuncSetAttribute(attn_prefill_kernel<HD, PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 		attr = true;
 	}
-	attn_prefill_kernel<HD><<<dim3(a.n_qt, a.n_heads), 128, smem, s>>>(a);
+	attn_prefill_kernel<HD, PRECISE><<<dim3(a.n_qt, a.n_heads), 128, smem, s>>>(a);
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "attn_prefill launch failed: %s", cudaGetErrorString(e));
 	return XALM_OK;
@@ -895,17 +1003,30 @@ int prefill_run(const PrefillModel& pm, PrefillScratch** scratch, const int* tok
 	if (c.head_dim != 64 && c.head_dim != 128) return set_error(XALM_ERR_UNSUPPORTED, "prefill: head_dim %d (64 or 128)", c.head_dim);
 	if (c.dim % 8 || c.hidden_dim % 8 || pm.q_dim % 8 || pm.kv_dim % 8) return set_error(XALM_ERR_UNSUPPORTED, "prefill: dims must be multiples of 8");
 	if (targets && want_logits != 2) return set_error(XALM_ERR_INVALID, "prefill: target probabilities need the logits of every position");
-	const int na = split == 2 ? 2 : 1;
+	for (int i = 0; i < n; i++)
+		if (tokens[i] < 0 || tokens[i] >= c.vocab_size) return set_error(XALM_ERR_INVALID, "prefill: token %d out of range", tokens[i]);
+	// split: 1 = fp16 x fp16; 2 = hi+lo activations; 3 = hi+lo activations AND weights AND attention operands (fp32-grade)
+	const int na = split >= 2 ? 2 : 1;
+	const bool precise = split >= 3;
 	cudaStream_t s = pm.stream;
 	if (!*scratch) *scratch = new PrefillScratch();
 	PrefillScratch& sc = **scratch;
+	if (!sc.side) {
+		XALM_CUDA_CHECK(cudaStreamCreateWithFlags(&sc.side, cudaStreamNonBlocking));
+		XALM_CUDA_CHECK(cudaEventCreateWithFlags(&sc.ev_start, cudaEventDisableTiming));
+		for (int i = 0; i < 2; i++) {
+			XALM_CUDA_CHECK(cudaEventCreateWithFlags(&sc.ev_deq[i], cudaEventDisableTiming));
+			XALM_CUDA_CHECK(cudaEventCreateWithFlags(&sc.ev_gemm[i], cudaEventDisableTiming));
+		}
+	}
+	cudaStream_t ds = sc.side;
 	int launches = 0;
 
 	const int T = n, MT = cdiv(T, GB_M), Tp = MT * GB_M;
 	const int KT_dim = cdiv(c.dim, GB_K), KT_q = cdiv(pm.q_dim, GB_K), KT_h = cdiv(c.hidden_dim, GB_K);
 	const int n_qkv = pm.q_dim + 2 * pm.kv_dim;
 	const int NT_qkv = cdiv(n_qkv, GB_N), NT_dim = cdiv(c.dim, GB_N), NT_glu = cdiv(c.hidden_dim, GB_N / 2), NT_cls = cdiv(c.vocab_size, GB_N);
-	// ---- scratch ----
+	// ---- scratch (grown on demand; (re)allocation synchronises, steady state does not) ----
 	XALM_TRY(sc.x.ensure((size_t) Tp * c.dim * 4, true, s));
 	XALM_TRY(sc.xb_hi.ensure((size_t) MT * KT_dim * A_TILE_BYTES, true, s));
 	XALM_TRY(sc.xb2_hi.ensure((size_t) MT * KT_q * A_TILE_BYTES, true, s));
@@ -916,9 +1037,14 @@ int prefill_run(const PrefillModel& pm, PrefillScratch** scratch, const int* tok
 		XALM_TRY(sc.hb_lo.ensure((size_t) MT * KT_h * A_TILE_BYTES, true, s));
 	}
 	XALM_TRY(sc.q.ensure((size_t) Tp * pm.q_dim * 2, true, s));
-	size_t wt_bytes = std::max({(size_t) NT_qkv * KT_dim, (size_t) NT_dim * KT_q, (size_t) NT_glu * KT_dim, (size_t) NT_dim * KT_h}) * B_TILE_BYTES;
-	if (want_logits) wt_bytes = std::max(wt_bytes, (size_t) NT_cls * KT_dim * B_TILE_BYTES);
-	XALM_TRY(sc.wt.ensure(wt_bytes, false, s));
+	if (precise) XALM_TRY(sc.q_lo.ensure((size_t) Tp * pm.q_dim * 2, true, s));
+	XALM_TRY(sc.rope.ensure((size_t) T * (c.head_dim / 2) * sizeof(float2), false, s));
+	size_t wt_tiles = std::max({(size_t) NT_qkv * KT_dim, (size_t) NT_dim * KT_q, (size_t) NT_glu * KT_dim, (size_t) NT_dim * KT_h});
+	if (want_logits) wt_tiles = std::max(wt_tiles, (size_t) NT_cls * KT_dim);
+	for (int i = 0; i < 2; i++) {
+		XALM_TRY(sc.wt[i].ensure(wt_tiles * B_TILE_BYTES, false, s));
+		if (precise) XALM_TRY(sc.wt_lo[i].ensure(wt_tiles * B_TILE_BYTES, false, s));
+	}
 	XALM_TRY(sc.tokens.ensure((size_t) T * 4, false, s));
 	// want 1: only the last M tile goes through the classifier; its valid rows are stored, the last one is the answer
 	const int logit_row0 = want_logits == 1 ? (MT - 1) * GB_M : 0;
@@ -931,62 +1057,93 @@ int prefill_run(const PrefillModel& pm, PrefillScratch** scratch, const int* tok
 	ATiles hb{sc.hb_hi.p, na == 2 ? sc.hb_lo.p : nullptr, KT_h};
 	float* x = reinterpret_cast<float*>(sc.x.p);
 	__half* q = reinterpret_cast<__half*>(sc.q.p);
+	__half* q_lo = precise ? reinterpret_cast<__half*>(sc.q_lo.p) : nullptr;
+	const float2* rope_cs = reinterpret_cast<const float2*>(sc.rope.p);
 
-	for (int i = 0; i < T; i++)
-		if (tokens[i] < 0 || tokens[i] >= c.vocab_size) return set_error(XALM_ERR_INVALID, "prefill: token %d out of range", tokens[i]);
+	// ---- weight dequantisation runs one GEMM ahead on the side stream, ping-ponging two tile buffers ----
+	XALM_CUDA_CHECK(cudaEventRecord(sc.ev_start, s));
+	XALM_CUDA_CHECK(cudaStreamWaitEvent(ds, sc.ev_start, 0));
+	int job = 0;      // GEMMs issued so far
+	int prepared = 0; // weight sets dequantised (issued) so far
+	auto nb_of = [&](const WMat& w) { return precise && w.type != XALM_F16 ? 2 : 1; }; // f16 weights are exact in one plane
+	auto prep = [&](const WMat& w, bool glu, int glu_off, int n_valid, int K, int NT, int KT) -> int {
+		const int b = prepared & 1;
+		if (prepared >= 2) XALM_CUDA_CHECK(cudaStreamWaitEvent(ds, sc.ev_gemm[b], 0)); // the GEMM that last read this buffer
+		XALM_TRY(launch_dequant_tiles(w, glu, glu_off, n_valid, K, NT, KT, sc.wt[b].p, nb_of(w) == 2 ? sc.wt_lo[b].p : nullptr, ds));
+		XALM_CUDA_CHECK(cudaEventRecord(sc.ev_deq[b], ds));
+		prepared++;
+		launches++;
+		return XALM_OK;
+	};
+	auto run = [&](GemmArgs& g, const WMat& w) -> int {
+		const int b = job & 1;
+		g.b = sc.wt[b].p;
+		g.b_lo = sc.wt_lo[b].p;
+		XALM_CUDA_CHECK(cudaStreamWaitEvent(s, sc.ev_deq[b], 0));
+		XALM_TRY(launch_gemm(g, na, nb_of(w), s));
+		XALM_CUDA_CHECK(cudaEventRecord(sc.ev_gemm[b], s));
+		job++;
+		launches++;
+		return XALM_OK;
+	};
+	const size_t L = pm.layers.size();
+	auto prep_qkv = [&](size_t l) { return prep(pm.layers[l].wqkv, false, 0, n_qkv, c.dim, NT_qkv, KT_dim); };
+
 	XALM_CUDA_CHECK(cudaMemcpyAsync(sc.tokens.p, tokens, (size_t) T * 4, cudaMemcpyHostToDevice, s));
 	embed_rows_kernel<<<std::min(cdiv(T * c.dim, 256), sm_count() * 8), 256, 0, s>>>(pm.embed_type, pm.embed_raw, pm.embed_row_bytes, c.dim,
 	                                                                                  reinterpret_cast<const int*>(sc.tokens.p), T, x);
-	launches++;
-	const int norm_grid = std::min(cdiv(T, 8), sm_count() * 4);
-	for (size_t l = 0; l < pm.layers.size(); l++) {
-		const PrefillLayer& L = pm.layers[l];
-		if (!prefill_type_ok(L.wqkv.type)) return set_error(XALM_ERR_UNSUPPORTED, "prefill: weight type %d", L.wqkv.type);
+	rope_table_kernel<<<std::min(cdiv(T * (c.head_dim / 2), 256), sm_count() * 8), 256, 0, s>>>(pm.rope_freq, c.head_dim / 2, T, pos0,
+	                                                                                             reinterpret_cast<float2*>(sc.rope.p));
+	launches += 2;
+	const int norm_grid = std::min(cdiv(T, 8), sm_count() * 8);
+	if (L) XALM_TRY(prep_qkv(0));
+	for (size_t l = 0; l < L; l++) {
+		const PrefillLayer& P = pm.layers[l];
+		if (!prefill_type_ok(P.wqkv.type)) return set_error(XALM_ERR_UNSUPPORTED, "prefill: weight type %d", P.wqkv.type);
 		// ---- attention half ----
-		rmsnorm_rows_kernel<<<norm_grid, 256, 0, s>>>(x, T, c.dim, L.rms_att, L.rms_att_type, c.norm_eps, xb);
-		XALM_TRY(launch_dequant_tiles(L.wqkv, false, 0, n_qkv, c.dim, NT_qkv, KT_dim, sc.wt.p, s));
+		rmsnorm_rows_kernel<<<norm_grid, 256, 0, s>>>(x, T, c.dim, P.rms_att, P.rms_att_type, c.norm_eps, xb);
+		XALM_TRY(prep(P.wo, false, 0, c.dim, pm.q_dim, NT_dim, KT_q));
 		GemmArgs g = {};
-		g.a_hi = xb.hi; g.a_lo = xb.lo; g.b = sc.wt.p;
+		g.a_hi = xb.hi; g.a_lo = xb.lo;
 		g.MT = MT; g.NT = NT_qkv; g.KT = KT_dim; g.mt0 = 0; g.M = T; g.N = n_qkv; g.epi = GEPI_QKV;
-		g.q_out = q; g.k_cache = L.k_cache; g.v_cache = L.v_cache; g.rope_freq = pm.rope_freq;
+		g.q_out = q; g.q_lo = q_lo; g.k_cache = P.k_cache; g.v_cache = P.v_cache; g.rope_cs = rope_cs;
 		g.q_dim = pm.q_dim; g.kv_dim = pm.kv_dim; g.head_dim = c.head_dim; g.pos0 = pos0; g.qkv_clip = c.qkv_clip;
-		XALM_TRY(launch_gemm(g, na, s));
-		AttnPArgs at = {q, L.k_cache, L.v_cache, xb2, T, pos0, pm.q_dim, pm.kv_dim, c.n_heads, c.n_kv_heads, cdiv(T, 64)};
-		if (c.head_dim == 128) XALM_TRY(launch_attn_p<128>(at, s));
-		else XALM_TRY(launch_attn_p<64>(at, s));
-		XALM_TRY(launch_dequant_tiles(L.wo, false, 0, c.dim, pm.q_dim, NT_dim, KT_q, sc.wt.p, s));
+		XALM_TRY(run(g, P.wqkv));
+		AttnPArgs at = {q, q_lo, P.k_cache, P.v_cache, xb2, T, pos0, pm.q_dim, pm.kv_dim, c.n_heads, c.n_kv_heads, cdiv(T, 64)};
+		if (c.head_dim == 128) XALM_TRY(precise ? (launch_attn_p<128, true>(at, s)) : (launch_attn_p<128, false>(at, s)));
+		else XALM_TRY(precise ? (launch_attn_p<64, true>(at, s)) : (launch_attn_p<64, false>(at, s)));
+		XALM_TRY(prep(P.w13, true, P.glu_off, c.hidden_dim, c.dim, NT_glu, KT_dim));
 		g = {};
-		g.a_hi = xb2.hi; g.a_lo = xb2.lo; g.b = sc.wt.p;
+		g.a_hi = xb2.hi; g.a_lo = xb2.lo;
 		g.MT = MT; g.NT = NT_dim; g.KT = KT_q; g.M = T; g.N = c.dim; g.epi = GEPI_RESID; g.out = x; g.ldo = c.dim;
-		XALM_TRY(launch_gemm(g, na, s));
+		XALM_TRY(run(g, P.wo));
 		// ---- feed-forward half ----
-		rmsnorm_rows_kernel<<<norm_grid, 256, 0, s>>>(x, T, c.dim, L.rms_ffn, L.rms_ffn_type, c.norm_eps, xb);
-		XALM_TRY(launch_dequant_tiles(L.w13, true, L.glu_off, c.hidden_dim, c.dim, NT_glu, KT_dim, sc.wt.p, s));
+		rmsnorm_rows_kernel<<<norm_grid, 256, 0, s>>>(x, T, c.dim, P.rms_ffn, P.rms_ffn_type, c.norm_eps, xb);
+		XALM_TRY(prep(P.w2, false, 0, c.dim, c.hidden_dim, NT_dim, KT_h));
 		g = {};
-		g.a_hi = xb.hi; g.a_lo = xb.lo; g.b = sc.wt.p;
+		g.a_hi = xb.hi; g.a_lo = xb.lo;
 		g.MT = MT; g.NT = NT_glu; g.KT = KT_dim; g.M = T; g.N = c.hidden_dim; g.epi = GEPI_GLU; g.o = hb; g.act = c.act;
-		XALM_TRY(launch_gemm(g, na, s));
-		XALM_TRY(launch_dequant_tiles(L.w2, false, 0, c.dim, c.hidden_dim, NT_dim, KT_h, sc.wt.p, s));
+		XALM_TRY(run(g, P.w13));
+		if (l + 1 < L) XALM_TRY(prep_qkv(l + 1));
+		else if (want_logits) XALM_TRY(prep(pm.wcls, false, 0, c.vocab_size, c.dim, NT_cls, KT_dim));
 		g = {};
-		g.a_hi = hb.hi; g.a_lo = hb.lo; g.b = sc.wt.p;
+		g.a_hi = hb.hi; g.a_lo = hb.lo;
 		g.MT = MT; g.NT = NT_dim; g.KT = KT_h; g.M = T; g.N = c.dim; g.epi = GEPI_RESID; g.out = x; g.ldo = c.dim;
-		XALM_TRY(launch_gemm(g, na, s));
-		launches += 11;
+		XALM_TRY(run(g, P.w2));
+		launches += 3;
 	}
 	if (want_logits) {
+		if (!L) XALM_TRY(prep(pm.wcls, false, 0, c.vocab_size, c.dim, NT_cls, KT_dim));
 		rmsnorm_rows_kernel<<<norm_grid, 256, 0, s>>>(x, T, c.dim, pm.rms_final, pm.rms_final_type, c.norm_eps, xb);
-		XALM_TRY(launch_dequant_tiles(pm.wcls, false, 0, c.vocab_size, c.dim, NT_cls, KT_dim, sc.wt.p, s));
 		GemmArgs g = {};
-		g.a_hi = xb.hi; g.a_lo = xb.lo; g.b = sc.wt.p;
+		g.a_hi = xb.hi; g.a_lo = xb.lo;
 		g.NT = NT_cls; g.KT = KT_dim; g.M = T; g.N = c.vocab_size; g.epi = GEPI_STORE;
 		g.out = reinterpret_cast<float*>(sc.logits.p); g.ldo = c.vocab_size;
 		g.mt0 = want_logits == 1 ? MT - 1 : 0;
 		g.MT = want_logits == 1 ? 1 : MT;
 		g.out_row0 = logit_row0;
-		XALM_TRY(launch_gemm(g, na, s));
-		launches += 3;
-		cudaError_t e = cudaGetLastError();
-		if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "prefill launch failed: %s", cudaGetErrorString(e));
+		XALM_TRY(run(g, pm.wcls));
+		launches++;
 		if (targets && probs_host) {
 			XALM_TRY(sc.targets.ensure((size_t) T * 4, false, s));
 			XALM_TRY(sc.probs.ensure((size_t) T * 4, false, s));
@@ -1016,57 +1173,59 @@ int prefill_run(const PrefillModel& pm, PrefillScratch** scratch, const int* tok
 int prefill_gemm_dev(const WMat& w, const float* a_dev, int T, float* out_dev, int split, cudaStream_t s) {
 	const int K = w.n, N = w.rows;
 	if (K % 8) return set_error(XALM_ERR_INVALID, "gemm: K %% 8 != 0");
-	const int na = split == 2 ? 2 : 1;
+	const int na = split >= 2 ? 2 : 1, nb = split >= 3 ? 2 : 1;
 	const int MT = cdiv(T, GB_M), KT = cdiv(K, GB_K), NT = cdiv(N, GB_N);
-	DevBuf ah, al, bt;
+	DevBuf ah, al, bt, bl;
 	XALM_TRY(ah.ensure((size_t) MT * KT * A_TILE_BYTES, true, s));
 	if (na == 2) XALM_TRY(al.ensure((size_t) MT * KT * A_TILE_BYTES, true, s));
 	XALM_TRY(bt.ensure((size_t) NT * KT * B_TILE_BYTES, false, s));
+	if (nb == 2) XALM_TRY(bl.ensure((size_t) NT * KT * B_TILE_BYTES, false, s));
 	ATiles at{ah.p, na == 2 ? al.p : nullptr, KT};
 	pack_a_kernel<<<std::min(cdiv(T * (K / 8), 256), sm_count() * 8), 256, 0, s>>>(a_dev, T, K, at);
-	int rc = launch_dequant_tiles(w, false, 0, N, K, NT, KT, bt.p, s);
+	int rc = launch_dequant_tiles(w, false, 0, N, K, NT, KT, bt.p, nb == 2 ? bl.p : nullptr, s);
 	if (rc == XALM_OK) {
 		GemmArgs g = {};
-		g.a_hi = at.hi; g.a_lo = at.lo; g.b = bt.p;
+		g.a_hi = at.hi; g.a_lo = at.lo; g.b = bt.p; g.b_lo = bl.p;
 		g.MT = MT; g.NT = NT; g.KT = KT; g.M = T; g.N = N; g.epi = GEPI_STORE; g.out = out_dev; g.ldo = N;
-		rc = launch_gemm(g, na, s);
+		rc = launch_gemm(g, na, nb, s);
 	}
 	cudaError_t e = cudaStreamSynchronize(s);
-	ah.release(); al.release(); bt.release();
+	ah.release(); al.release(); bt.release(); bl.release();
 	if (rc != XALM_OK) return rc;
 	if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "gemm failed: %s", cudaGetErrorString(e));
 	return XALM_OK;
 }
 
 int prefill_bench_gemm(int T, int N, int K, int split, int iters, float* ms_per_launch) {
-	const int na = split == 2 ? 2 : 1;
+	const int na = split >= 2 ? 2 : 1, nb = split >= 3 ? 2 : 1;
 	const int MT = cdiv(T, GB_M), KT = cdiv(K, GB_K), NT = cdiv(N, GB_N);
 	cudaStream_t s;
 	XALM_CUDA_CHECK(cudaStreamCreate(&s));
-	DevBuf ah, al, bt, out;
+	DevBuf ah, al, bt, bl, out;
 	XALM_TRY(ah.ensure((size_t) MT * KT * A_TILE_BYTES, true, s));
 	if (na == 2) XALM_TRY(al.ensure((size_t) MT * KT * A_TILE_BYTES, true, s));
 	XALM_TRY(bt.ensure((size_t) NT * KT * B_TILE_BYTES, true, s));
+	if (nb == 2) XALM_TRY(bl.ensure((size_t) NT * KT * B_TILE_BYTES, true, s));
 	XALM_TRY(out.ensure((size_t) MT * GB_M * N * 4, true, s));
 	// fill the operands with a pattern of small finite fp16 values (0x2C00 = 0.0625)
 	XALM_CUDA_CHECK(cudaMemsetAsync(ah.p, 0x2C, (size_t) MT * KT * A_TILE_BYTES, s));
 	XALM_CUDA_CHECK(cudaMemsetAsync(bt.p, 0x2C, (size_t) NT * KT * B_TILE_BYTES, s));
 	GemmArgs g = {};
-	g.a_hi = ah.p; g.a_lo = al.p; g.b = bt.p;
+	g.a_hi = ah.p; g.a_lo = al.p; g.b = bt.p; g.b_lo = bl.p;
 	g.MT = MT; g.NT = NT; g.KT = KT; g.M = T; g.N = N; g.epi = GEPI_STORE; g.out = reinterpret_cast<float*>(out.p); g.ldo = N;
 	cudaEvent_t e0, e1;
 	XALM_CUDA_CHECK(cudaEventCreate(&e0));
 	XALM_CUDA_CHECK(cudaEventCreate(&e1));
-	for (int i = 0; i < 3; i++) XALM_TRY(launch_gemm(g, na, s));
+	for (int i = 0; i < 3; i++) XALM_TRY(launch_gemm(g, na, nb, s));
 	XALM_CUDA_CHECK(cudaEventRecord(e0, s));
-	for (int i = 0; i < iters; i++) XALM_TRY(launch_gemm(g, na, s));
+	for (int i = 0; i < iters; i++) XALM_TRY(launch_gemm(g, na, nb, s));
 	XALM_CUDA_CHECK(cudaEventRecord(e1, s));
 	XALM_CUDA_CHECK(cudaStreamSynchronize(s));
 	float ms = 0.f;
 	XALM_CUDA_CHECK(cudaEventElapsedTime(&ms, e0, e1));
 	*ms_per_launch = ms / (float) iters;
 	cudaEventDestroy(e0); cudaEventDestroy(e1);
-	ah.release(); al.release(); bt.release(); out.release();
+	ah.release(); al.release(); bt.release(); bl.release(); out.release();
 	cudaStreamDestroy(s);
 	return XALM_OK;
 }
