@@ -185,6 +185,151 @@ def workload_config(args, cfg) -> dict:
             "parallelism": f"tp{args.gpus}"}
 
 
+def measured_peak_tflops() -> tuple:
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["bf16_tflops"]), float(d["bf16_tflops_sustained"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 1590.0, 1400.0, "fallback (B200_PROFILING.md)"
+
+
+def gemm_flops(cfg: dict, T: int, with_cls: bool = True) -> float:
+    """2*T*(weights that enter a GEMM): the seven per-layer contractions + the classifier (2*T*7.11e9 for m7)."""
+    q_dim, kv_dim = cfg["n_heads"] * cfg["head_dim"], cfg["n_kv_heads"] * cfg["head_dim"]
+    per_layer = cfg["dim"] * (q_dim + 2 * kv_dim) + q_dim * cfg["dim"] + 3 * cfg["dim"] * cfg["hidden_dim"]
+    return 2.0 * T * (cfg["n_layers"] * per_layer + (cfg["vocab_size"] * cfg["dim"] if with_cls else 0))
+
+
+def run_perplexity_workload(args):
+    """BASELINE config[2]: perplexity mode on a 4k-token synthetic input.  A step = one batched pass over `--tokens` positions
+    (every position's logits + softmax-at-target), weights resident.  `value` device-timed; `e2e` through Model.prefill with
+    host tokens in and host probabilities out.  --impl reference: the oracle's token-at-a-time loop on a bounded sample."""
+    from xalm_b200 import synth, types as T, xalm_file as X
+    cfg_full = synth.model_config(args.shape)
+    cfg = X.parse_config(synth.metadata_strings(cfg_full), args.ctx)
+    wtype = T.parse(args.wtype)
+    n_tok = min(args.tokens, cfg["max_seq_len"])
+    rng = np.random.default_rng(321)
+    toks = rng.integers(3, cfg["vocab_size"], size=n_tok + 1).astype(np.int32)
+    config = {"workload": f"{args.shape} ({'Mistral-7B-v0.2' if args.shape == 'm7' else args.shape} architecture) random-init {args.wtype}, "
+                          f"perplexity mode over a {n_tok}-token synthetic input (batched prefill, dequantised weights on tcgen05 GEMMs)",
+              "shape": args.shape, "weight_format": args.wtype, "tokens_per_step": n_tok, "context": cfg["max_seq_len"],
+              "l2": "inputs larger than L2 (7.5 GB of weights + 0.5 GB of logits per step)", "parallelism": "tp1"}
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) != 0:
+            return
+        from oracle import oracle
+        cores = oracle.set_threads(os.cpu_count() or 1)
+        synth.set_threads(cores)
+        tensors = {name: (t.id, np.ascontiguousarray(arr).view(np.uint8).reshape(-1)) for name, t, arr in synth.iter_tensors(cfg_full, wtype, args.seed)}
+        om = oracle.OracleModel(cfg, tensors, acc_mode=1)
+        n = max(1, args.steps)
+        for i in range(max(1, args.warmup)):
+            om.forward(int(toks[i]), i, 1)
+        t0 = time.perf_counter()
+        s = 0.0
+        for i in range(n):
+            lg = om.forward(int(toks[i]), i, 1)
+            s += float(np.log(oracle.sample_prob(lg, int(toks[i + 1]))))
+        dt = time.perf_counter() - t0
+        tps = n / dt
+        sample = f"positions 0..{n - 1} of the same input, one Model::forward + sample_prob each (main.cpp:244-254), wall clock"
+        print(json.dumps({"impl": "reference", "metric": "perplexity_tokens_per_s", "value": tps, "unit": "tok/s", "n_gpus": args.gpus,
+                          "steps": n, "warmup": args.warmup, "ms_per_step": dt / n * 1e3, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": tps, "unit": "tok/s", "cores": cores, "kind": "port", "sample": sample},
+                          "e2e": {"value": tps, "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}), flush=True)
+        return
+
+    import torch
+    from xalm_b200 import capi
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the backend has no CPU fallback")
+    if args.gpus != 1:
+        raise SystemExit("the perplexity workload is single-GPU (the batched prefill path does not shard yet)")
+    torch.cuda.set_device(0)
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    keep_host = not args.no_cpu_baseline
+    synth.set_threads(os.cpu_count() or 8)
+    model, host_tensors = build_model_streaming(cfg_full, cfg, wtype, args.seed, keep_host, device=0, stream=tstream.cuda_stream)
+    split = args.split or 3
+    capi.tune("prefill_split", split)
+    steps, warm = max(1, args.steps), max(3, args.warmup)
+    for _ in range(warm):
+        model.prefill_async(toks[:-1], 0, 2)
+    model.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(0) as clocks:
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            model.prefill_async(toks[:-1], 0, 2)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        launches = model.last_launch_count() * steps
+        # end to end: host tokens + targets in, host probabilities out, log + mean on the host (main.cpp:251-258)
+        for _ in range(2):
+            model.prefill(toks[:-1], 0, want_logits=2, targets=toks[1:], fetch_logits=False)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            _, probs = model.prefill(toks[:-1], 0, want_logits=2, targets=toks[1:], fetch_logits=False)
+            ppl = float(np.exp(-np.mean(np.log(probs))))
+        e2e_s = time.perf_counter() - t0
+    tps = n_tok * steps / (ms / 1e3)
+    e2e_tps = n_tok * steps / e2e_s
+    burst, sustained, src = measured_peak_tflops()
+    # dominant kernel: the fused gate|up GEMM (2*T*2*hidden*dim flops), timed alone
+    N13, K13 = 2 * cfg["hidden_dim"], cfg["dim"]
+    k_ms = capi.bench_gemm(n_tok, N13, K13, split, 20)
+    mmas = {1: 1, 2: 2, 3: 3}[split]
+    k_tf = 2.0 * n_tok * N13 * K13 / (k_ms / 1e3) / 1e12
+    step_tf = gemm_flops(cfg, n_tok) * steps / (ms / 1e3) / 1e12
+    # accuracy of this mode against the token-at-a-time decode kernels on the same KV prefix (last 4 positions)
+    from xalm_b200.model import InferenceState
+    lg_all = model.prefill(toks[:-1], 0, want_logits=2)
+    st = InferenceState(cfg).cuda()
+    worst = 0.0
+    for pos in range(n_tok - 4, n_tok):
+        model.forward(st, int(toks[pos]), pos, 1)
+        worst = max(worst, float(np.max(np.abs(st.logits() - lg_all[pos]))))
+    line = {
+        "metric": "perplexity_tokens_per_s", "value": tps, "unit": "tok/s", "n_gpus": 1, "steps": steps, "warmup": warm,
+        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f16 operands (hi+lo pairs) / f32 accumulate" if split == 3 else "f16 operands / f32 accumulate", "data": "synthetic", "config": config,
+        "e2e": {"value": e2e_tps, "unit": "tok/s", "h2d_bytes_per_step": int(2 * n_tok * 4), "d2h_bytes_per_step": int(n_tok * 4),
+                "perplexity": ppl},
+        "gpu_launches": launches, "clocks": clocks.summary(),
+        "roofline": {"bound": "tensor", "achieved": k_tf, "peak": burst, "unit": "TFLOP/s", "frac": k_tf / burst, "traffic": None,
+                     "kernel": f"gemm_tc_kernel (tcgen05, 128x256x64 tiles) gate|up {n_tok}x{N13}x{K13}", "ms_per_launch": k_ms,
+                     "mma_per_product": mmas, "issued_tflops": k_tf * mmas, "issued_frac": k_tf * mmas / burst, "peak_source": src,
+                     "note": "achieved counts ALGORITHMIC flops 2*T*N*K; precision mode 3 issues 3 fp16 MMAs per product (hi.hi + lo.hi + hi.lo)"},
+        "step_roofline": {"flops_per_step": gemm_flops(cfg, n_tok), "achieved": step_tf, "peak": sustained, "unit": "TFLOP/s",
+                          "frac": step_tf / sustained, "note": "GEMM flops only (attention excluded) over the whole step vs the sustained cuBLAS figure"},
+        "accuracy": {"max_abs_logit_diff_vs_decode_path": worst, "positions": 4, "tolerance": 1e-2, "prefill_split": split},
+    }
+    if keep_host:
+        from oracle import oracle
+        cores = oracle.set_threads(os.cpu_count() or 1)
+        om = oracle.OracleModel(cfg, host_tensors, acc_mode=1)
+        om.forward(int(toks[0]), 0, 1)
+        n = args.cpu_tokens
+        t0 = time.perf_counter()
+        for i in range(n):
+            lg = om.forward(int(toks[i]), i, 1)
+            oracle.sample_prob(lg, int(toks[i + 1]))
+        cdt = time.perf_counter() - t0
+        om.close()
+        line["cpu_baseline"] = {"value": n / cdt, "unit": "tok/s", "cores": cores, "kind": "port",
+                                "sample": f"positions 0..{n - 1} of the same input, one forward + sample_prob each, wall clock"}
+    print(json.dumps(line), flush=True)
+    model.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -197,9 +342,16 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-tokens", type=int, default=6, help="tokens the CPU baseline decodes (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="decode", choices=["decode", "perplexity"],
+                    help="decode = BASELINE config[1] (the headline metric); perplexity = config[2]: batched prefill of a 4k-token input")
+    ap.add_argument("--tokens", type=int, default=4096, help="perplexity workload: tokens per step")
+    ap.add_argument("--split", type=int, default=0, help="perplexity workload: operand precision (0 = library default 3; 1 = plain fp16)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
+    if args.workload == "perplexity":
+        run_perplexity_workload(args)
+        return
     if args.impl == "reference":
         run_reference(args)
         return

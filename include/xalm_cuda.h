@@ -121,8 +121,10 @@ int xalm_cuda_sync(xalm_cuda_model* m);
  * every position), 1 = logits of the last position -> logits_host[vocab], 2 = every position -> logits_host[n*vocab].
  * targets/probs_host (n entries each, or NULL; needs want_logits 2): probs_host[i] = Sampler::sample_prob(targets[i])
  * on the logits of position pos0+i (sampler.cpp:18-33) — what perplexity mode takes the log of (main.cpp:251).
- * logits_host may be NULL.  Synchronous.  Tensor operands are fp16 (fp32 accumulate): logits agree with the
- * token-at-a-time path within the north star's 1e-2. */
+ * logits_host may be NULL.  Synchronous.  Tensor-core operands are fp16 with fp32 accumulation; the "prefill_split"
+ * knob (xalm_cuda_tune) picks how fp32 values enter them: 3 (default) = hi+lo fp16 pairs for activations, weights and the
+ * attention operands (3 MMAs per product; 32-layer 4k-token logits within ~1e-3 of the token-at-a-time path), 2 = pairs
+ * for activations only, 1 = plain fp16 (fastest; ~4e-2 at that depth).  North star tolerance: 1e-2. */
 int xalm_cuda_prefill(xalm_cuda_model* m, const int* tokens, int n, int pos0, int want_logits, float* logits_host,
                       const int* targets, float* probs_host);
 /* Enqueue only (no read-back, no host sync) — bench.py's device-timed leg. */

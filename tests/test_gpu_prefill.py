@@ -88,7 +88,7 @@ def test_prefill_logits_match_oracle(wtype, shape, n, split):
                 assert np.max(np.abs(a - b)) <= 1e-2 * max(1.0, float(np.abs(b).max()))
         gm.close(); om.close()
     finally:
-        capi.tune("prefill_split", 1)
+        capi.tune("prefill_split", 3)
 
 
 def test_prefill_then_decode_and_last_logits():

@@ -8,6 +8,7 @@
 //     (the reference's usage text already says "default - cuda", main.cpp:24);
 //   * run_completion honours -d (the reference drops it, main.cpp:44,537);
 //   * elapsed time is wall clock (the reference divides by user+system CPU time, main.cpp:101,117).
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -68,7 +69,18 @@ void run_completion(const std::string& checkpoint_path, const std::string& promp
 
 	t0 = now_s();
 	size_t read_bytes = 0;
-	for (size_t pos = 0; pos < encoding.size(); pos++) { // hydrate the KV cache (main.cpp:94-100)
+	// hydrate the KV cache (main.cpp:94-100).  The reference walks the prompt token by token; here the part of the prompt
+	// that fits the cache without wrapping goes through ONE batched pass (tcgen05 GEMMs), the rest through the same loop.
+	size_t pos = 0;
+	if (getenv("XALM_NO_PREFILL") == nullptr && encoding.size() > 1) {
+		const size_t n = std::min(encoding.size(), (size_t) model.config.max_seq_len);
+		const InferenceMode mode = n == encoding.size() ? InferenceMode::OUTPUT_LOGITS : InferenceMode::HYDRATE_KV_CACHE;
+		if (model.prefill(state, encoding.data(), (int) n, 0, mode)) {
+			read_bytes += model.active_bytes(n - 1); // the weights are streamed once for the whole batch
+			pos = n;
+		}
+	}
+	for (; pos < encoding.size(); pos++) {
 		const InferenceMode mode = pos + 1 == encoding.size() ? InferenceMode::OUTPUT_LOGITS : InferenceMode::HYDRATE_KV_CACHE;
 		model.forward(state, encoding[pos], (int) pos, mode);
 		read_bytes += model.active_bytes(pos);
@@ -109,7 +121,26 @@ void run_perplexity(const std::string& checkpoint_path, const std::string& promp
 	const double t0 = now_s();
 	size_t read_bytes = 0;
 	const size_t N = encoding.size() - 1;
-	for (size_t pos = 0; pos + 1 < encoding.size(); pos++) { // main.cpp:244-254 — same token-at-a-time loop as the reference
+	size_t pos = 0;
+	// main.cpp:244-254 evaluates one position per forward; positions that fit the cache without wrapping are evaluated in
+	// batched passes of up to 4096 (every position's logits on the device, softmax-at-target there too), the rest as before.
+	if (getenv("XALM_NO_PREFILL") == nullptr) {
+		std::vector<float> probs;
+		while (pos < N && pos < (size_t) model.config.max_seq_len) {
+			const size_t n = std::min({N - pos, (size_t) model.config.max_seq_len - pos, (size_t) 4096});
+			probs.resize(n);
+			if (!model.prefill(state, encoding.data() + pos, (int) n, (int) pos, InferenceMode::OUTPUT_LOGITS, encoding.data() + pos + 1, probs.data())) break;
+			std::cout << "\r Computing perplexity..." << pos + n << "/" << N << std::flush;
+			read_bytes += model.active_bytes(pos + n - 1);
+			for (size_t i = 0; i < n; i++) {
+				const double logprob = std::log(probs[i]);
+				sum_logprob += logprob;
+				ss_logprob += logprob * logprob;
+			}
+			pos += n;
+		}
+	}
+	for (; pos + 1 < encoding.size(); pos++) {
 		std::cout << "\r Computing perplexity..." << pos + 1 << "/" << N << std::flush;
 		model.forward(state, encoding[pos], (int) pos);
 		read_bytes += model.active_bytes(pos);

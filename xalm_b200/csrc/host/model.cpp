@@ -201,7 +201,7 @@ xalm_config Config::to_c() const {
 InferenceState::InferenceState(const Config& config) : own_logits_((size_t) config.vocab_size, 0.f) {}
 
 // ---- Model -------------------------------------------------------------------------------------------------------
-Model::Model(Model&& o) noexcept : config(o.config), device(o.device), host_(std::move(o.host_)), types_(std::move(o.types_)), handle_(o.handle_) {
+Model::Model(Model&& o) noexcept : config(o.config), device(o.device), host_(std::move(o.host_)), types_(std::move(o.types_)), handle_(o.handle_), tp_size_(o.tp_size_) {
 	o.handle_ = nullptr;
 }
 Model::~Model() {
@@ -250,6 +250,7 @@ void Model::cuda(int device_index, int tp_rank, int tp_size, const void* comm_id
 	if (handle_) return;
 	const xalm_config c = config.to_c();
 	if (xalm_cuda_create(&c, device_index, tp_rank, tp_size, &handle_) != XALM_OK) xalm_throw_last("model.cuda()");
+	tp_size_ = tp_size;
 	if (tp_size > 1) {
 		if (!comm_id) throw std::invalid_argument("model.cuda(): tensor parallel needs a communicator id");
 		if (xalm_cuda_comm_init(handle_, comm_id) != XALM_OK) xalm_throw_last("model.cuda()");
@@ -293,6 +294,24 @@ void Model::forward(const InferenceState& s, const int token, const int pos, con
 		std::fprintf(stderr, "Model::forward: %s\n", xalm_cuda_last_error());
 		std::abort();
 	}
+}
+
+bool Model::prefill(const InferenceState& s, const int* tokens, const int n, const int pos0, const InferenceMode mode, const int* targets,
+                    float* probs) const {
+	if (device != Device::CUDA || !handle_)
+		throw std::runtime_error("Model::prefill: model is not on a CUDA device (call model.cuda()); this backend has no CPU path");
+	if (n <= 0 || pos0 < 0 || (long long) pos0 + n > config.max_seq_len || tp_size_ > 1) return false;
+	if (!s.logits_ptr_ && s.device == Device::CUDA) s.logits_ptr_ = xalm_cuda_logits_host(handle_);
+	int rc;
+	if (targets && probs) rc = xalm_cuda_prefill(handle_, tokens, n, pos0, 2, nullptr, targets, probs);
+	else if (mode == InferenceMode::OUTPUT_LOGITS) rc = xalm_cuda_prefill(handle_, tokens, n, pos0, 1, s.logits(), nullptr, nullptr);
+	else rc = xalm_cuda_prefill(handle_, tokens, n, pos0, 0, nullptr, nullptr, nullptr);
+	if (rc == XALM_ERR_UNSUPPORTED) return false; // e.g. a head_dim the batched attention kernel does not take
+	if (rc != XALM_OK) {
+		std::fprintf(stderr, "Model::prefill: %s\n", xalm_cuda_last_error());
+		std::abort();
+	}
+	return true;
 }
 
 // ---- Sampler (sampler.cpp:3-30) ----------------------------------------------------------------------------------

@@ -137,12 +137,19 @@ struct Model {
 	void cuda(int device_index = 0, int tp_rank = 0, int tp_size = 1, const void* comm_id = nullptr);
 	[[nodiscard]] size_t active_bytes(size_t pos) const;
 	void forward(const InferenceState& s, int token, int pos, InferenceMode mode = InferenceMode::OUTPUT_LOGITS) const;
+	// The per-position loops of main.cpp:94-100 / :244-254 as one batched pass on the tensor cores (xalm_cuda_prefill).
+	// Positions pos0 .. pos0+n-1; mode OUTPUT_LOGITS leaves the LAST position's logits in s.logits().  With `targets` and
+	// `probs` (n entries) also returns Sampler::sample_prob(targets[i]) at every position.  Returns false — and does nothing —
+	// when the batch cannot take this path (ring-buffer wrap past max_seq_len, tensor-parallel shard): callers fall back to forward().
+	bool prefill(const InferenceState& s, const int* tokens, int n, int pos0, InferenceMode mode = InferenceMode::OUTPUT_LOGITS,
+	             const int* targets = nullptr, float* probs = nullptr) const;
 
 private:
 	explicit Model(const Config& c) : config(c) {}
 	std::map<std::string, Tensor> host_; // until cuda()
 	std::map<std::string, Type> types_;  // kept for active_bytes after the host copies are gone
 	xalm_cuda_model* handle_ = nullptr;
+	int tp_size_ = 1;
 };
 
 // ---- Sampler (sampler.h / sampler.cpp): host-side, unchanged semantics incl. the FLT_MIN seed ---

@@ -32,6 +32,7 @@
 #include <stdio.h>
 
 #include <algorithm>
+#include <string>
 #include <vector>
 
 #include "matvec.cuh"
@@ -476,6 +477,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmArgs
 					}
 				}
 			} else if (g.epi == GEPI_QKV) {
+				// 16 columns = 8 rotation pairs at a time; q_dim, kv_dim and head_dim are multiples of 16, so a chunk never straddles
+				// the q | k | v regions or a head, and leaves as two 16-byte stores
 				const int pos = g.pos0 + m;
 				const float2* cs_row = g.rope_cs + (size_t) (mrow ? m : 0) * (g.head_dim / 2);
 				for (int c = 0; c < GB_N; c += 16) {
@@ -483,30 +486,37 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmArgs
 					tmem_ld16(taddr + c, v);
 					const int n0 = nt * GB_N + c;
 					if (!mrow || n0 >= g.N) continue;
+					const int region = n0 < g.q_dim ? 0 : (n0 < g.q_dim + g.kv_dim ? 1 : 2);
+					const int j0 = n0 - (region == 0 ? 0 : region == 1 ? g.q_dim : g.q_dim + g.kv_dim); // column inside the region
 #pragma unroll
-					for (int i = 0; i < 16; i += 2) {
-						const int n = n0 + i;
-						if (n >= g.N) break;
-						float v0 = clipf(v[i], g.qkv_clip), v1 = clipf(v[i + 1], g.qkv_clip); // infer.cpp:389-399
-						if (n < g.q_dim + g.kv_dim) { // rope (infer.cpp:305-322) on q and k: same sincosf(pos * freq) values as the decode kernels
-							const int j = (n < g.q_dim ? n : n - g.q_dim) % g.head_dim;
-							const float2 cs = cs_row[j >> 1];
-							const float a0 = v0, b0 = v1;
-							v0 = a0 * cs.x - b0 * cs.y;
-							v1 = a0 * cs.y + b0 * cs.x;
+					for (int i = 0; i < 16; i++) v[i] = clipf(v[i], g.qkv_clip); // infer.cpp:389-399
+					if (region < 2) { // rope (infer.cpp:305-322) on q and k: the same sincosf(pos * freq) values as the decode kernels
+						const float4* cs4 = reinterpret_cast<const float4*>(cs_row + ((j0 % g.head_dim) >> 1));
+#pragma unroll
+						for (int i = 0; i < 4; i++) {
+							const float4 t = cs4[i]; // {cos, sin} of two consecutive pairs
+							const float a0 = v[4 * i], b0 = v[4 * i + 1], a1 = v[4 * i + 2], b1 = v[4 * i + 3];
+							v[4 * i] = a0 * t.x - b0 * t.y; v[4 * i + 1] = a0 * t.y + b0 * t.x;
+							v[4 * i + 2] = a1 * t.z - b1 * t.w; v[4 * i + 3] = a1 * t.w + b1 * t.z;
 						}
-						const __half2 h = __floats2half2_rn(v0, v1);
-						if (n < g.q_dim) {
-							*reinterpret_cast<__half2*>(g.q_out + (size_t) m * g.q_dim + n) = h;
-							if (g.q_lo) {
-								const float2 f = __half22float2(h);
-								*reinterpret_cast<__half2*>(g.q_lo + (size_t) m * g.q_dim + n) = __floats2half2_rn(v0 - f.x, v1 - f.y);
-							}
-						} else if (n < g.q_dim + g.kv_dim) {
-							*reinterpret_cast<__half2*>(g.k_cache + (size_t) pos * g.kv_dim + (n - g.q_dim)) = h;
-						} else {
-							*reinterpret_cast<__half2*>(g.v_cache + (size_t) pos * g.kv_dim + (n - g.q_dim - g.kv_dim)) = h;
+					}
+					__half2 h[8];
+#pragma unroll
+					for (int i = 0; i < 8; i++) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+					__half* dst = region == 0 ? g.q_out + (size_t) m * g.q_dim + j0
+					            : region == 1 ? g.k_cache + (size_t) pos * g.kv_dim + j0 : g.v_cache + (size_t) pos * g.kv_dim + j0;
+					reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<const uint4*>(h)[0];
+					reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<const uint4*>(h)[1];
+					if (region == 0 && g.q_lo) {
+						__half2 l[8];
+#pragma unroll
+						for (int i = 0; i < 8; i++) {
+							const float2 f = __half22float2(h[i]);
+							l[i] = __floats2half2_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
 						}
+						uint4* dl = reinterpret_cast<uint4*>(g.q_lo + (size_t) m * g.q_dim + j0);
+						dl[0] = reinterpret_cast<const uint4*>(l)[0];
+						dl[1] = reinterpret_cast<const uint4*>(l)[1];
 					}
 				}
 			} else {
@@ -1001,7 +1011,7 @@ int prefill_run(const PrefillModel& pm, PrefillScratch** scratch, const int* tok
 		return set_error(XALM_ERR_INVALID, "prefill: positions [%d, %d) do not fit the %d-slot KV cache without wrapping (use forward)", pos0,
 		                 pos0 + n, c.max_seq_len);
 	if (c.head_dim != 64 && c.head_dim != 128) return set_error(XALM_ERR_UNSUPPORTED, "prefill: head_dim %d (64 or 128)", c.head_dim);
-	if (c.dim % 8 || c.hidden_dim % 8 || pm.q_dim % 8 || pm.kv_dim % 8) return set_error(XALM_ERR_UNSUPPORTED, "prefill: dims must be multiples of 8");
+	if (c.dim % 16 || c.hidden_dim % 16 || pm.q_dim % 16 || pm.kv_dim % 16) return set_error(XALM_ERR_UNSUPPORTED, "prefill: dims must be multiples of 16");
 	if (targets && want_logits != 2) return set_error(XALM_ERR_INVALID, "prefill: target probabilities need the logits of every position");
 	for (int i = 0; i < n; i++)
 		if (tokens[i] < 0 || tokens[i] >= c.vocab_size) return set_error(XALM_ERR_INVALID, "prefill: token %d out of range", tokens[i]);
@@ -1019,8 +1029,19 @@ int prefill_run(const PrefillModel& pm, PrefillScratch** scratch, const int* tok
 			XALM_CUDA_CHECK(cudaEventCreateWithFlags(&sc.ev_gemm[i], cudaEventDisableTiming));
 		}
 	}
-	cudaStream_t ds = sc.side;
+	const bool timing = getenv("XALM_PREFILL_TIMING") != nullptr; // per-category CUDA-event timing, everything on one stream
+	cudaStream_t ds = timing ? s : sc.side;
 	int launches = 0;
+	struct Span { const char* what; cudaEvent_t a, b; };
+	std::vector<Span> spans;
+	auto t_begin = [&](const char* what) {
+		if (!timing) return;
+		Span sp{what, nullptr, nullptr};
+		cudaEventCreate(&sp.a); cudaEventCreate(&sp.b);
+		cudaEventRecord(sp.a, s);
+		spans.push_back(sp);
+	};
+	auto t_end = [&]() { if (timing) cudaEventRecord(spans.back().b, s); };
 
 	const int T = n, MT = cdiv(T, GB_M), Tp = MT * GB_M;
 	const int KT_dim = cdiv(c.dim, GB_K), KT_q = cdiv(pm.q_dim, GB_K), KT_h = cdiv(c.hidden_dim, GB_K);
@@ -1069,7 +1090,9 @@ int prefill_run(const PrefillModel& pm, PrefillScratch** scratch, const int* tok
 	auto prep = [&](const WMat& w, bool glu, int glu_off, int n_valid, int K, int NT, int KT) -> int {
 		const int b = prepared & 1;
 		if (prepared >= 2) XALM_CUDA_CHECK(cudaStreamWaitEvent(ds, sc.ev_gemm[b], 0)); // the GEMM that last read this buffer
+		t_begin("dequant");
 		XALM_TRY(launch_dequant_tiles(w, glu, glu_off, n_valid, K, NT, KT, sc.wt[b].p, nb_of(w) == 2 ? sc.wt_lo[b].p : nullptr, ds));
+		t_end();
 		XALM_CUDA_CHECK(cudaEventRecord(sc.ev_deq[b], ds));
 		prepared++;
 		launches++;
@@ -1080,7 +1103,9 @@ int prefill_run(const PrefillModel& pm, PrefillScratch** scratch, const int* tok
 		g.b = sc.wt[b].p;
 		g.b_lo = sc.wt_lo[b].p;
 		XALM_CUDA_CHECK(cudaStreamWaitEvent(s, sc.ev_deq[b], 0));
+		t_begin(g.epi == GEPI_QKV ? "gemm_qkv" : g.epi == GEPI_GLU ? "gemm_w13" : g.epi == GEPI_STORE ? "gemm_cls" : g.KT == KT_q ? "gemm_wo" : "gemm_w2");
 		XALM_TRY(launch_gemm(g, na, nb_of(w), s));
+		t_end();
 		XALM_CUDA_CHECK(cudaEventRecord(sc.ev_gemm[b], s));
 		job++;
 		launches++;
@@ -1101,7 +1126,9 @@ int prefill_run(const PrefillModel& pm, PrefillScratch** scratch, const int* tok
 		const PrefillLayer& P = pm.layers[l];
 		if (!prefill_type_ok(P.wqkv.type)) return set_error(XALM_ERR_UNSUPPORTED, "prefill: weight type %d", P.wqkv.type);
 		// ---- attention half ----
+		t_begin("rmsnorm");
 		rmsnorm_rows_kernel<<<norm_grid, 256, 0, s>>>(x, T, c.dim, P.rms_att, P.rms_att_type, c.norm_eps, xb);
+		t_end();
 		XALM_TRY(prep(P.wo, false, 0, c.dim, pm.q_dim, NT_dim, KT_q));
 		GemmArgs g = {};
 		g.a_hi = xb.hi; g.a_lo = xb.lo;
@@ -1110,15 +1137,19 @@ int prefill_run(const PrefillModel& pm, PrefillScratch** scratch, const int* tok
 		g.q_dim = pm.q_dim; g.kv_dim = pm.kv_dim; g.head_dim = c.head_dim; g.pos0 = pos0; g.qkv_clip = c.qkv_clip;
 		XALM_TRY(run(g, P.wqkv));
 		AttnPArgs at = {q, q_lo, P.k_cache, P.v_cache, xb2, T, pos0, pm.q_dim, pm.kv_dim, c.n_heads, c.n_kv_heads, cdiv(T, 64)};
+		t_begin("attention");
 		if (c.head_dim == 128) XALM_TRY(precise ? (launch_attn_p<128, true>(at, s)) : (launch_attn_p<128, false>(at, s)));
 		else XALM_TRY(precise ? (launch_attn_p<64, true>(at, s)) : (launch_attn_p<64, false>(at, s)));
+		t_end();
 		XALM_TRY(prep(P.w13, true, P.glu_off, c.hidden_dim, c.dim, NT_glu, KT_dim));
 		g = {};
 		g.a_hi = xb2.hi; g.a_lo = xb2.lo;
 		g.MT = MT; g.NT = NT_dim; g.KT = KT_q; g.M = T; g.N = c.dim; g.epi = GEPI_RESID; g.out = x; g.ldo = c.dim;
 		XALM_TRY(run(g, P.wo));
 		// ---- feed-forward half ----
+		t_begin("rmsnorm");
 		rmsnorm_rows_kernel<<<norm_grid, 256, 0, s>>>(x, T, c.dim, P.rms_ffn, P.rms_ffn_type, c.norm_eps, xb);
+		t_end();
 		XALM_TRY(prep(P.w2, false, 0, c.dim, c.hidden_dim, NT_dim, KT_h));
 		g = {};
 		g.a_hi = xb.hi; g.a_lo = xb.lo;
@@ -1166,6 +1197,22 @@ int prefill_run(const PrefillModel& pm, PrefillScratch** scratch, const int* tok
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "prefill launch failed: %s", cudaGetErrorString(e));
 	if (n_launches) *n_launches = launches;
+	if (timing) {
+		cudaStreamSynchronize(s);
+		std::vector<std::pair<std::string, float>> tot;
+		for (auto& sp : spans) {
+			float ms = 0.f;
+			cudaEventElapsedTime(&ms, sp.a, sp.b);
+			bool found = false;
+			for (auto& t : tot)
+				if (t.first == sp.what) { t.second += ms; found = true; }
+			if (!found) tot.push_back({sp.what, ms});
+			cudaEventDestroy(sp.a); cudaEventDestroy(sp.b);
+		}
+		fprintf(stderr, "[prefill timing, T=%d split=%d]", T, split);
+		for (auto& t : tot) fprintf(stderr, " %s %.2f ms;", t.first.c_str(), t.second);
+		fprintf(stderr, "\n");
+	}
 	return XALM_OK;
 }
 

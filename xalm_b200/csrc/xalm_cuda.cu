@@ -67,7 +67,8 @@ static std::map<std::string, int>& tuning() {
 	    {"tma_rc", 0},       // 0 = auto, else force rows per tile (4 or 8)
 	    {"tma_ns_max", 4},   // most ring stages
 	    {"tma_ctas_per_sm", 2},
-	    {"prefill_split", 1}, // batched prefill: 1 = fp16 activations, 2 = hi+lo fp16 pair (two MMAs per weight tile)
+	    {"prefill_split", 3}, // batched prefill operand precision: 1 = fp16 x fp16 (fastest; logits drift ~4e-2 over 32 layers), 2 = hi+lo fp16
+	                          // activations, 3 = hi+lo on activations, weights and attention operands (default: logits within ~1e-3 of the decode path)
 	};
 	return t;
 }

@@ -150,16 +150,17 @@ class Model:
         capi.check(capi.lib().xalm_cuda_sync(self._h))
 
     # ---- batched prefill: the per-position loops of main.cpp:94-100 / :244-254 in one pass (tcgen05 GEMMs) ----
-    def prefill(self, tokens, pos0: int = 0, want_logits: int = 1, targets=None):
+    def prefill(self, tokens, pos0: int = 0, want_logits: int = 1, targets=None, fetch_logits: bool = True):
         """Positions pos0..pos0+len(tokens)-1 at once.  want_logits 0: hydrate only -> None; 1: logits of the last
         position (vocab,); 2: all positions (n, vocab).  With `targets` returns (logits, probs) where probs[i] is
-        Sampler.sample_prob(targets[i]) at position pos0+i."""
+        Sampler.sample_prob(targets[i]) at position pos0+i; fetch_logits=False leaves the logits on the device (perplexity
+        mode needs only the probabilities)."""
         if self._h is None:
             raise RuntimeError("Model.prefill: the model is not on a CUDA device (call model.cuda()); this backend has no CPU path")
         tok = np.ascontiguousarray(tokens, dtype=np.int32)
         n = int(tok.size)
         V = self.config["vocab_size"]
-        lg = None if want_logits == 0 else np.empty(V if want_logits == 1 else (n, V), dtype=np.float32)
+        lg = None if want_logits == 0 or not fetch_logits else np.empty(V if want_logits == 1 else (n, V), dtype=np.float32)
         tg = pr = None
         if targets is not None:
             tg = np.ascontiguousarray(targets, dtype=np.int32)
