@@ -113,13 +113,14 @@ def test_prefill_then_decode_and_last_logits():
     gm.close(); om.close()
 
 
-def test_chunked_prefill_and_hydrate_mode():
-    config, om, gm = synth_pair("tiny", "f16", seed=10, std=0.06)
-    tokens = np.random.default_rng(3).integers(3, config["vocab_size"], size=120).astype(np.int32)
+@pytest.mark.parametrize("shape,n,cut", [("tiny", 120, 50), ("small", 300, 130)])   # head_dim 64: mma.sync attention; 128: tcgen05 attention
+def test_chunked_prefill_and_hydrate_mode(shape, n, cut):
+    config, om, gm = synth_pair(shape, "f16", seed=10, std=0.06 if shape == "tiny" else 0.03)
+    tokens = np.random.default_rng(3).integers(3, config["vocab_size"], size=n).astype(np.int32)
     ref = _oracle_all_logits(om, tokens)
-    assert gm.prefill(tokens[:50], 0, want_logits=0) is None            # hydrate only
-    got = gm.prefill(tokens[50:], 50, want_logits=2)                   # second chunk attends to the first through the cache
-    assert np.max(np.abs(got - ref[50:])) <= LOGIT_TOL
+    assert gm.prefill(tokens[:cut], 0, want_logits=0) is None          # hydrate only
+    got = gm.prefill(tokens[cut:], cut, want_logits=2)                 # second chunk attends to the first through the cache
+    assert np.max(np.abs(got - ref[cut:])) <= LOGIT_TOL
     with pytest.raises(capi.XalmError):                                 # would wrap the ring: not a prefill job
         gm.prefill(tokens, config["max_seq_len"] - 10, want_logits=0)
     gm.close(); om.close()

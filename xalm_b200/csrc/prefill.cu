@@ -309,6 +309,36 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
 	for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
+// issue only (no wait): lets several loads fly before one tmem_wait_ld()
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, float* v) {
+	uint32_t r[32];
+	asm volatile(
+	    "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+	    "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+	    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+	      "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+	      "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+	      "=r"(r[30]), "=r"(r[31])
+	    : "r"(taddr));
+#pragma unroll
+	for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+	asm volatile(
+	    "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+	    "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+	    "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+	    "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])),
+	    "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])),
+	    "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])), "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])),
+	    "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])), "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])),
+	    "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])), "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])),
+	    "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])), "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])),
+	    "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+	    : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
 	uint32_t r[8];
 	__syncwarp();
@@ -345,6 +375,9 @@ struct GemmArgs {
 	// QKV
 	__half* q_out;      // (T, q_dim) row-major fp16, RoPE applied
 	__half* q_lo;       // fp16 of what q_out's rounding dropped (precise mode), or nullptr
+	uint8_t* qt_hi;     // when set: q goes into 128-row x 64-column operand tiles ((head, row block, hd half) order) for attn_tc_kernel
+	uint8_t* qt_lo;     // instead of row-major q_out / q_lo
+	int n_qb;           // row blocks of 128
 	__half* k_cache;
 	__half* v_cache;
 	const float2* rope_cs; // (T, head_dim/2): {cos, sin}(pos * freq) per row, from rope_table_kernel
@@ -503,6 +536,24 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmArgs
 					__half2 h[8];
 #pragma unroll
 					for (int i = 0; i < 8; i++) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+					if (region == 0 && g.qt_hi) { // head_dim 128: tile ((head * n_qb + m / 128) * 2 + hd half), row m % 128
+						const int head = j0 >> 7, hc = j0 & 127;
+						const size_t toff = ((size_t) (head * g.n_qb + (m >> 7)) * 2 + (hc >> 6)) * A_TILE_BYTES;
+						const size_t o0 = toff + tile_inner_off(m & 127, hc & 63), o1 = toff + tile_inner_off(m & 127, (hc & 63) + 8);
+						*reinterpret_cast<uint4*>(g.qt_hi + o0) = reinterpret_cast<const uint4*>(h)[0];
+						*reinterpret_cast<uint4*>(g.qt_hi + o1) = reinterpret_cast<const uint4*>(h)[1];
+						if (g.qt_lo) {
+							__half2 l[8];
+#pragma unroll
+							for (int i = 0; i < 8; i++) {
+								const float2 f = __half22float2(h[i]);
+								l[i] = __floats2half2_rn(v[2 * i] - f.x, v[2 * i + 1] - f.y);
+							}
+							*reinterpret_cast<uint4*>(g.qt_lo + o0) = reinterpret_cast<const uint4*>(l)[0];
+							*reinterpret_cast<uint4*>(g.qt_lo + o1) = reinterpret_cast<const uint4*>(l)[1];
+						}
+						continue;
+					}
 					__half* dst = region == 0 ? g.q_out + (size_t) m * g.q_dim + j0
 					            : region == 1 ? g.k_cache + (size_t) pos * g.kv_dim + j0 : g.v_cache + (size_t) pos * g.kv_dim + j0;
 					reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<const uint4*>(h)[0];
@@ -878,6 +929,272 @@ __global__ void __launch_bounds__(128) attn_prefill_kernel(const AttnPArgs a) {
 	}
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// causal attention on tcgen05 (head_dim 128): S = Q K^T and O_blk = P V as UMMA 128x128x16 tiles with accumulators in TMEM.
+//   Q operand   tiles written by the QKV epilogue: (head, 128-row block, hd half) -> 128 rows x 64
+//   K operand   tiles (kv head, 128-key block, hd half) -> 128 keys x 64            } retile_kv_kernel, once per layer, from the
+//   V^T operand tiles (kv head, 128-key block, key half) -> 128 hd rows x 64 keys   } fp16 cache rows [0, pos0 + T)
+// One CTA = 128 query rows of one head.  warp 0: bulk-copy producer (Q once; one K slot and one V slot — K and V are needed
+// at different times, so single slots already overlap load and use).  warp 1: MMA issuer; QK of block j+1 is issued before
+// it waits for P of block j (S is double-buffered in TMEM).  warps 2-5: softmax, thread = query row: two passes over S in
+// TMEM (row max, then exp), P as fp16 (hi, lo) into a shared-memory operand tile, running (max, sum) and the fp32 output
+// row in registers; O_blk comes back from TMEM one block later and is folded in with the rescale.
+// ------------------------------------------------------------------------------------------------------------------
+struct AttnTcArgs {
+	const uint8_t* qt_hi;
+	const uint8_t* qt_lo;
+	const uint8_t* kt;   // K tiles
+	const uint8_t* vt;   // V^T tiles
+	ATiles o;            // xb2
+	int T, pos0, n_heads, n_kv_heads, n_qb, n_kb_total;
+};
+
+// cache rows -> K tiles and V^T tiles.  grid (64-key blocks, kv heads), 256 threads.
+__global__ void __launch_bounds__(256) retile_kv_kernel(const __half* __restrict__ k_cache, const __half* __restrict__ v_cache, int kv_dim,
+                                                        int kv_total, int n_kb_total, uint8_t* __restrict__ kt, uint8_t* __restrict__ vt) {
+	__shared__ __align__(16) __half sv[64][136];
+	const int kb64 = blockIdx.x, kvh = blockIdx.y;
+	const int key0 = kb64 * 64;
+	const int kb = kb64 >> 1, half = kb64 & 1; // 128-key block and which half of it
+	// K: 64 keys x 128 hd -> rows [64*half, 64*half+64) of tiles (kvh, kb, 0) and (kvh, kb, 1)
+	uint8_t* ktile = kt + ((size_t) (kvh * n_kb_total + kb) * 2) * A_TILE_BYTES;
+	for (int i = threadIdx.x; i < 64 * 16; i += 256) {
+		const int r = i >> 4, c = i & 15; // key row, 16-byte chunk of the 128 hd values
+		const int key = key0 + r;
+		uint4 kvv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+		if (key < kv_total) {
+			kvv = *reinterpret_cast<const uint4*>(k_cache + (size_t) key * kv_dim + kvh * 128 + c * 8);
+			vv = *reinterpret_cast<const uint4*>(v_cache + (size_t) key * kv_dim + kvh * 128 + c * 8);
+		}
+		*reinterpret_cast<uint4*>(ktile + (size_t) (c >> 3) * A_TILE_BYTES + tile_inner_off(half * 64 + r, (c & 7) * 8)) = kvv;
+		*reinterpret_cast<uint4*>(&sv[r][c * 8]) = vv;
+	}
+	__syncthreads();
+	// V^T: tile (kvh, kb, half): row = hd d, columns = these 64 keys
+	uint8_t* vtile = vt + ((size_t) (kvh * n_kb_total + kb) * 2 + half) * A_TILE_BYTES;
+	for (int i = threadIdx.x; i < 128 * 8; i += 256) {
+		const int d = i & 127, c = i >> 7; // chunk c = keys 8c .. 8c+7
+		__half h[8];
+#pragma unroll
+		for (int j = 0; j < 8; j++) h[j] = sv[c * 8 + j][d];
+		*reinterpret_cast<uint4*>(vtile + tile_inner_off(d, c * 8)) = *reinterpret_cast<const uint4*>(h);
+	}
+}
+
+constexpr int ATT_THREADS = 192;
+template <bool PRECISE>
+struct AttnTcCfg {
+	static constexpr int NP = PRECISE ? 2 : 1;                 // operand planes for Q and P
+	static constexpr int Q_BYTES = NP * 2 * A_TILE_BYTES;      // 128 rows x 128 hd
+	static constexpr int P_BYTES = NP * 2 * A_TILE_BYTES;      // 128 rows x 128 keys
+	static constexpr int KV_BYTES = 2 * A_TILE_BYTES;          // one K block or one V^T block
+	static constexpr size_t SMEM = Q_BYTES + P_BYTES + 2 * KV_BYTES + 1024 + 256;
+};
+
+template <bool PRECISE>
+__global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const AttnTcArgs a) {
+	using Cfg = AttnTcCfg<PRECISE>;
+	constexpr int NP = Cfg::NP;
+	extern __shared__ uint8_t smem_raw[];
+	const uint32_t raw_s = s_u32(smem_raw);
+	uint8_t* smem = smem_raw + (((raw_s + 1023u) & ~1023u) - raw_s);
+	uint8_t* sQ = smem;
+	uint8_t* sP = sQ + Cfg::Q_BYTES;
+	uint8_t* sK = sP + Cfg::P_BYTES;
+	uint8_t* sV = sK + Cfg::KV_BYTES;
+	uint64_t* bars = reinterpret_cast<uint64_t*>(sV + Cfg::KV_BYTES);
+	uint64_t* q_full = bars;          // tx
+	uint64_t* k_full = bars + 1;      // tx
+	uint64_t* k_empty = bars + 2;     // commit
+	uint64_t* v_full = bars + 3;      // tx
+	uint64_t* v_empty = bars + 4;     // commit
+	uint64_t* s_full = bars + 5;      // [2] commit
+	uint64_t* s_empty = bars + 7;     // [2] 4 softmax warps
+	uint64_t* p_full = bars + 9;      // 4 softmax warps
+	uint64_t* o_full = bars + 10;     // commit
+	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int qb = a.n_qb - 1 - (int) blockIdx.x; // longest first
+	const int h = blockIdx.y;
+	const int kvh = h / (a.n_heads / a.n_kv_heads);
+	const int q0 = qb * 128;
+	const int q_last = min(q0 + 128, a.T) - 1;
+	const int n_kb = (a.pos0 + q_last) / 128 + 1; // 128-key blocks any row of this tile sees
+
+	if (threadIdx.x == 0) {
+		mb_init(q_full, 1); mb_init(k_full, 1); mb_init(k_empty, 1); mb_init(v_full, 1); mb_init(v_empty, 1);
+		mb_init(&s_full[0], 1); mb_init(&s_full[1], 1); mb_init(&s_empty[0], 4); mb_init(&s_empty[1], 4);
+		mb_init(p_full, 4); mb_init(o_full, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	if (warp == 1) tmem_alloc(tmem_slot, 512);
+	tc_fence_before();
+	__syncthreads();
+	tc_fence_after();
+	const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
+	const uint32_t TM_S0 = tmem_base, TM_O = tmem_base + 256; // S[b] at columns 128*b, O_blk at 256
+
+	if (warp == 0) {
+		if (lane == 0) {
+			const size_t qoff = ((size_t) (h * a.n_qb + qb) * 2) * A_TILE_BYTES;
+			mb_expect_tx(q_full, Cfg::Q_BYTES);
+			bulk_load(sQ, a.qt_hi + qoff, 2 * A_TILE_BYTES, q_full);
+			if (PRECISE) bulk_load(sQ + 2 * A_TILE_BYTES, a.qt_lo + qoff, 2 * A_TILE_BYTES, q_full);
+			for (int j = 0; j < n_kb; j++) {
+				const size_t off = ((size_t) (kvh * a.n_kb_total + j) * 2) * A_TILE_BYTES;
+				mb_wait(k_empty, (j & 1) ^ 1);
+				mb_expect_tx(k_full, Cfg::KV_BYTES);
+				bulk_load(sK, a.kt + off, Cfg::KV_BYTES, k_full);
+				mb_wait(v_empty, (j & 1) ^ 1);
+				mb_expect_tx(v_full, Cfg::KV_BYTES);
+				bulk_load(sV, a.vt + off, Cfg::KV_BYTES, v_full);
+			}
+		}
+		__syncwarp();
+	} else if (warp == 1) {
+		if (lane == 0) {
+			constexpr uint32_t idesc = instr_desc_f16(128, 128);
+			const uint32_t q_s = s_u32(sQ), p_s = s_u32(sP), k_s = s_u32(sK), v_s = s_u32(sV);
+			auto issue_qk = [&](int j) {
+				const int b = j & 1;
+				mb_wait(k_full, j & 1);
+				mb_wait(&s_empty[b], ((j >> 1) & 1) ^ 1);
+				tc_fence_after();
+#pragma unroll
+				for (int p = 0; p < NP; p++)
+#pragma unroll
+					for (int t = 0; t < 2; t++) // hd halves
+#pragma unroll
+						for (int k = 0; k < 4; k++)
+							umma_f16(TM_S0 + 128 * b, smem_desc(q_s + (p * 2 + t) * A_TILE_BYTES) + 2 * k, smem_desc(k_s + t * A_TILE_BYTES) + 2 * k, idesc,
+							         (uint32_t) ((p | t | k) != 0));
+				umma_commit(k_empty);
+				umma_commit(&s_full[b]);
+			};
+			mb_wait(q_full, 0);
+			issue_qk(0);
+			for (int j = 0; j < n_kb; j++) {
+				if (j + 1 < n_kb) issue_qk(j + 1);
+				mb_wait(p_full, j & 1);
+				mb_wait(v_full, j & 1);
+				tc_fence_after();
+#pragma unroll
+				for (int p = 0; p < NP; p++)
+#pragma unroll
+					for (int t = 0; t < 2; t++) // key halves
+#pragma unroll
+						for (int k = 0; k < 4; k++)
+							umma_f16(TM_O, smem_desc(p_s + (p * 2 + t) * A_TILE_BYTES) + 2 * k, smem_desc(v_s + t * A_TILE_BYTES) + 2 * k, idesc,
+							         (uint32_t) ((j | p | t | k) != 0)); // O accumulates in TMEM over all key blocks
+				umma_commit(v_empty);
+				umma_commit(o_full);
+			}
+		}
+		__syncwarp();
+	} else {
+		const int quad = warp & 3;
+		const int r = quad * 32 + lane; // query row inside the tile = TMEM lane
+		const int row = q0 + r;
+		const uint32_t lane_addr = (uint32_t) (quad * 32) << 16;
+		const float scale = 1.0f / sqrtf(128.0f);
+		// The output accumulates in TMEM (PV with accumulate); it is rescaled only when a row's maximum grows by more than TAU
+		// over the maximum its probabilities are currently expressed against (exp(TAU) = 2981 still fits fp16 comfortably).
+		constexpr float TAU = 8.0f;
+		float m_run = -INFINITY, l_run = 0.f;
+		for (int j = 0; j < n_kb; j++) {
+			const int b = j & 1;
+			mb_wait(&s_full[b], (j >> 1) & 1);
+			tc_fence_after();
+			const bool need_mask = j * 128 + 127 > a.pos0 + q0; // some key of this block is beyond the tile's first row
+			const int lim = a.pos0 + row - j * 128;              // keys with index (inside the block) > lim are masked
+			float sv[128];
+			__syncwarp();
+#pragma unroll
+			for (int c = 0; c < 4; c++) tmem_ld32_issue(TM_S0 + lane_addr + 128 * b + 32 * c, sv + 32 * c);
+			tmem_wait_ld();
+			float mx = -INFINITY;
+#pragma unroll
+			for (int i = 0; i < 128; i++) {
+				float t = sv[i] * scale;
+				if (need_mask && i > lim) t = -INFINITY;
+				sv[i] = t;
+				mx = fmaxf(mx, t);
+			}
+			if (j > 0) mb_wait(o_full, (j - 1) & 1); // P V of the previous block has completed: the P tile is free, O is quiescent
+			const bool grow = mx > m_run + TAU;       // block 0: m_run = -inf -> true, but there is nothing to rescale yet
+			if (j == 0) m_run = mx;
+			else if (__any_sync(0xffffffffu, grow)) {
+				const float m_new = grow ? mx : m_run;
+				const float corr = __expf(m_run - m_new); // 1 for the rows that keep their maximum
+				tc_fence_after();
+#pragma unroll
+				for (int c = 0; c < 4; c++) {
+					float v[32];
+					tmem_ld32(TM_O + lane_addr + 32 * c, v);
+#pragma unroll
+					for (int i = 0; i < 32; i++) v[i] *= corr;
+					tmem_st32(TM_O + lane_addr + 32 * c, v);
+				}
+				tmem_wait_st();
+				l_run *= corr;
+				m_run = m_new;
+			}
+			// ---- probabilities -> fp16 operand tile (hi, lo), row sum ----
+			float rs = 0.f;
+#pragma unroll
+			for (int g8 = 0; g8 < 16; g8++) { // 8 keys = one 16-byte chunk
+				__half2 hh[4], ll[4];
+#pragma unroll
+				for (int i = 0; i < 4; i++) {
+					const float p0 = __expf(sv[8 * g8 + 2 * i] - m_run), p1 = __expf(sv[8 * g8 + 2 * i + 1] - m_run);
+					rs += p0 + p1;
+					hh[i] = __floats2half2_rn(p0, p1);
+					if (PRECISE) {
+						const float2 f = __half22float2(hh[i]);
+						ll[i] = __floats2half2_rn(p0 - f.x, p1 - f.y);
+					}
+				}
+				const int key = 8 * g8; // inside the 128-key block
+				const size_t off = (size_t) (key >> 6) * A_TILE_BYTES + tile_inner_off(r, key & 63);
+				*reinterpret_cast<uint4*>(sP + off) = *reinterpret_cast<const uint4*>(hh);
+				if (PRECISE) *reinterpret_cast<uint4*>(sP + 2 * A_TILE_BYTES + off) = *reinterpret_cast<const uint4*>(ll);
+			}
+			l_run += rs;
+			tc_fence_before();
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes of P -> visible to the MMA (async proxy)
+			__syncwarp();
+			if (lane == 0) {
+				mb_arrive(&s_empty[b]);
+				mb_arrive(p_full);
+			}
+		}
+		mb_wait(o_full, (n_kb - 1) & 1);
+		tc_fence_after();
+		const float inv = 1.0f / l_run;
+#pragma unroll
+		for (int c = 0; c < 4; c++) {
+			float v[32];
+			tmem_ld32(TM_O + lane_addr + 32 * c, v);
+			if (row < a.T) {
+#pragma unroll
+				for (int g8 = 0; g8 < 4; g8++) {
+					float out[8];
+#pragma unroll
+					for (int i = 0; i < 8; i++) out[i] = v[8 * g8 + i] * inv;
+					store_a8(a.o, row, h * 128 + 32 * c + 8 * g8, out);
+				}
+			}
+		}
+	}
+	tc_fence_before();
+	__syncthreads();
+	if (warp == 1) {
+		tc_fence_after();
+		tmem_dealloc(tmem_base, 512);
+	}
+}
+
 // fp32 row-major (T, K) -> A tiles (op-level hook and tests)
 __global__ void pack_a_kernel(const float* __restrict__ a, int T, int K, ATiles o) {
 	const size_t total = (size_t) T * (K / 8);
@@ -927,7 +1244,7 @@ struct DevBuf {
 };
 
 struct PrefillScratch {
-	DevBuf x, xb_hi, xb_lo, xb2_hi, xb2_lo, hb_hi, hb_lo, q, q_lo, wt[2], wt_lo[2], logits, tokens, targets, probs, rope;
+	DevBuf x, xb_hi, xb_lo, xb2_hi, xb2_lo, hb_hi, hb_lo, q, q_lo, wt[2], wt_lo[2], logits, tokens, targets, probs, rope, qt_hi, qt_lo, kt, vt;
 	int logits_rows = 0;
 	cudaStream_t side = nullptr;          // dequantises the NEXT GEMM's weights while the current GEMM runs
 	cudaEvent_t ev_start = nullptr, ev_deq[2] = {nullptr, nullptr}, ev_gemm[2] = {nullptr, nullptr};
@@ -936,7 +1253,7 @@ struct PrefillScratch {
 void prefill_free(PrefillScratch* s) {
 	if (!s) return;
 	DevBuf* all[] = {&s->x, &s->xb_hi, &s->xb_lo, &s->xb2_hi, &s->xb2_lo, &s->hb_hi, &s->hb_lo, &s->q, &s->q_lo, &s->wt[0], &s->wt[1],
-	                 &s->wt_lo[0], &s->wt_lo[1], &s->logits, &s->tokens, &s->targets, &s->probs, &s->rope};
+	                 &s->wt_lo[0], &s->wt_lo[1], &s->logits, &s->tokens, &s->targets, &s->probs, &s->rope, &s->qt_hi, &s->qt_lo, &s->kt, &s->vt};
 	for (DevBuf* b : all) b->release();
 	if (s->side) cudaStreamDestroy(s->side);
 	if (s->ev_start) cudaEventDestroy(s->ev_start);
@@ -987,6 +1304,19 @@ static int launch_dequant_tiles(const WMat& w, bool glu, int glu_off, int n_vali
 static bool prefill_type_ok(int t) {
 	TypeInfo ti;
 	return type_info(t, &ti);
+}
+
+template <bool PRECISE>
+static int launch_attn_tc(const AttnTcArgs& a, cudaStream_t s) {
+	static bool attr = false;
+	if (!attr) {
+		XALM_CUDA_CHECK(cudaFuncSetAttribute(attn_tc_kernel<PRECISE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) AttnTcCfg<PRECISE>::SMEM));
+		attr = true;
+	}
+	attn_tc_kernel<PRECISE><<<dim3(a.n_qb, a.n_heads), ATT_THREADS, AttnTcCfg<PRECISE>::SMEM, s>>>(a);
+	cudaError_t e = cudaGetLastError();
+	if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "attn_tc launch failed: %s", cudaGetErrorString(e));
+	return XALM_OK;
 }
 
 template <int HD, bool PRECISE>
@@ -1057,8 +1387,18 @@ int prefill_run(const PrefillModel& pm, PrefillScratch** scratch, const int* tok
 		XALM_TRY(sc.xb2_lo.ensure((size_t) MT * KT_q * A_TILE_BYTES, true, s));
 		XALM_TRY(sc.hb_lo.ensure((size_t) MT * KT_h * A_TILE_BYTES, true, s));
 	}
-	XALM_TRY(sc.q.ensure((size_t) Tp * pm.q_dim * 2, true, s));
-	if (precise) XALM_TRY(sc.q_lo.ensure((size_t) Tp * pm.q_dim * 2, true, s));
+	// head_dim 128: attention on tcgen05 (attn_tc_kernel); otherwise the mma.sync kernel on row-major q
+	const bool attn_tc = c.head_dim == 128 && getenv("XALM_ATTN_MMA_SYNC") == nullptr;
+	const int n_qb = MT, n_kb_total = cdiv(pos0 + T, 128);
+	if (attn_tc) {
+		XALM_TRY(sc.qt_hi.ensure((size_t) c.n_heads * n_qb * 2 * A_TILE_BYTES, true, s));
+		if (precise) XALM_TRY(sc.qt_lo.ensure((size_t) c.n_heads * n_qb * 2 * A_TILE_BYTES, true, s));
+		XALM_TRY(sc.kt.ensure((size_t) c.n_kv_heads * n_kb_total * 2 * A_TILE_BYTES, false, s));
+		XALM_TRY(sc.vt.ensure((size_t) c.n_kv_heads * n_kb_total * 2 * A_TILE_BYTES, false, s));
+	} else {
+		XALM_TRY(sc.q.ensure((size_t) Tp * pm.q_dim * 2, true, s));
+		if (precise) XALM_TRY(sc.q_lo.ensure((size_t) Tp * pm.q_dim * 2, true, s));
+	}
 	XALM_TRY(sc.rope.ensure((size_t) T * (c.head_dim / 2) * sizeof(float2), false, s));
 	size_t wt_tiles = std::max({(size_t) NT_qkv * KT_dim, (size_t) NT_dim * KT_q, (size_t) NT_glu * KT_dim, (size_t) NT_dim * KT_h});
 	if (want_logits) wt_tiles = std::max(wt_tiles, (size_t) NT_cls * KT_dim);
@@ -1135,11 +1475,19 @@ int prefill_run(const PrefillModel& pm, PrefillScratch** scratch, const int* tok
 		g.MT = MT; g.NT = NT_qkv; g.KT = KT_dim; g.mt0 = 0; g.M = T; g.N = n_qkv; g.epi = GEPI_QKV;
 		g.q_out = q; g.q_lo = q_lo; g.k_cache = P.k_cache; g.v_cache = P.v_cache; g.rope_cs = rope_cs;
 		g.q_dim = pm.q_dim; g.kv_dim = pm.kv_dim; g.head_dim = c.head_dim; g.pos0 = pos0; g.qkv_clip = c.qkv_clip;
+		if (attn_tc) { g.qt_hi = sc.qt_hi.p; g.qt_lo = precise ? sc.qt_lo.p : nullptr; g.n_qb = n_qb; }
 		XALM_TRY(run(g, P.wqkv));
-		AttnPArgs at = {q, q_lo, P.k_cache, P.v_cache, xb2, T, pos0, pm.q_dim, pm.kv_dim, c.n_heads, c.n_kv_heads, cdiv(T, 64)};
 		t_begin("attention");
-		if (c.head_dim == 128) XALM_TRY(precise ? (launch_attn_p<128, true>(at, s)) : (launch_attn_p<128, false>(at, s)));
-		else XALM_TRY(precise ? (launch_attn_p<64, true>(at, s)) : (launch_attn_p<64, false>(at, s)));
+		if (attn_tc) {
+			retile_kv_kernel<<<dim3(2 * n_kb_total, c.n_kv_heads), 256, 0, s>>>(P.k_cache, P.v_cache, pm.kv_dim, pos0 + T, n_kb_total, sc.kt.p, sc.vt.p);
+			AttnTcArgs at = {sc.qt_hi.p, precise ? sc.qt_lo.p : nullptr, sc.kt.p, sc.vt.p, xb2, T, pos0, c.n_heads, c.n_kv_heads, n_qb, n_kb_total};
+			XALM_TRY(precise ? launch_attn_tc<true>(at, s) : launch_attn_tc<false>(at, s));
+			launches++;
+		} else {
+			AttnPArgs at = {q, q_lo, P.k_cache, P.v_cache, xb2, T, pos0, pm.q_dim, pm.kv_dim, c.n_heads, c.n_kv_heads, cdiv(T, 64)};
+			if (c.head_dim == 128) XALM_TRY(precise ? (launch_attn_p<128, true>(at, s)) : (launch_attn_p<128, false>(at, s)));
+			else XALM_TRY(precise ? (launch_attn_p<64, true>(at, s)) : (launch_attn_p<64, false>(at, s)));
+		}
 		t_end();
 		XALM_TRY(prep(P.w13, true, P.glu_off, c.hidden_dim, c.dim, NT_glu, KT_dim));
 		g = {};
