@@ -33,6 +33,8 @@ struct AttnArgs {
 	float* part_acc;       // (n_kv_heads, n_splits, G, HD)
 	float* part_ml;        // (n_kv_heads, n_splits, G, 2)
 	unsigned int* tickets; // (n_kv_heads,) zero-initialised, self-resetting
+	const uint8_t* pf_ptr; // first bytes of the next kernel's weights (Wo), pulled into L2 before this kernel waits for q
+	unsigned long long pf_bytes;
 };
 
 __host__ __device__ inline int attn_split_len(int kv_len, int n_splits, int min_split) {
@@ -55,6 +57,7 @@ __global__ void __launch_bounds__(NW * 32) attn_decode_kernel(const AttnArgs a) 
 	pdl_launch_dependents();
 	int tl = -1;
 	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) tl = tl_begin(300);
+	if (threadIdx.x == 0) l2_prefetch_slice(a.pf_ptr, a.pf_bytes, (int) (blockIdx.y * gridDim.x + blockIdx.x), (int) (gridDim.x * gridDim.y));
 	pdl_wait();
 	tl_mark(tl, 2);
 

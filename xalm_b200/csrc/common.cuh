@@ -66,6 +66,16 @@ __device__ __forceinline__ float4 ld_act4(const float* p) { return *reinterpret_
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 
+// ---- L2 prefetch of a slice of the NEXT kernel's first bytes (cp.async.bulk.prefetch.L2): CTA `cta` of `n_ctas` takes its share ----
+__device__ __forceinline__ void l2_prefetch_slice(const uint8_t* ptr, unsigned long long bytes, int cta, int n_ctas) {
+	if (!ptr || !bytes) return;
+	unsigned long long per = ((bytes + n_ctas - 1) / n_ctas + 127ull) & ~127ull;
+	const unsigned long long off = per * (unsigned long long) cta;
+	if (off >= bytes) return;
+	if (off + per > bytes) per = (bytes - off) & ~15ull;
+	if (per) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(ptr + off), "r"((unsigned int) per) : "memory");
+}
+
 // ---- packed fp32x2 arithmetic (new on sm_100: two FMAs per issued instruction) ---------------------------
 struct f32x2 {
 	unsigned long long v;

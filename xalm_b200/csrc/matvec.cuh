@@ -50,6 +50,11 @@ struct MatvecArgs {
 	float qkv_clip;
 	// one-byte LUT formats
 	int lut_type;        // 0 = none, else the type id whose 256 values fill the shared-memory table
+	// tail prefetch: when this CTA's producer has issued its last weight load it pulls its share of the NEXT kernel's first
+	// bytes into L2, so that kernel's ramp-up reads hit L2 instead of paying an HBM round trip after the dependency wait
+	const uint8_t* pf_ptr;       // next kernel's weights (or nullptr)
+	unsigned long long pf_bytes;
+	int pf_kv;                   // 1: also prefetch rows [0, kv_len) of k_cache / v_cache (the attention kernel that follows QKV)
 	// L2 prefetcher hand-shake (prefetch.cuh): block 0 publishes "kernel #prog_idx of this token has started"
 	unsigned int* progress;
 	int prog_idx;

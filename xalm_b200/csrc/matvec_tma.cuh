@@ -260,6 +260,12 @@ __global__ void __launch_bounds__((TMA_NW + 1) * 32, 1) matvec_tma_kernel(const 
 					if (++slot == NS) { slot = 0; phase ^= 1; }
 				}
 			}
+			l2_prefetch_slice(a.pf_ptr, a.pf_bytes, (int) blockIdx.x, (int) gridDim.x);
+			if (a.pf_kv) {
+				const unsigned long long kvb = (unsigned long long) a.step->kv_len * a.kv_dim * sizeof(__half);
+				l2_prefetch_slice(reinterpret_cast<const uint8_t*>(a.k_cache), kvb, (int) blockIdx.x, (int) gridDim.x);
+				l2_prefetch_slice(reinterpret_cast<const uint8_t*>(a.v_cache), kvb, (int) blockIdx.x, (int) gridDim.x);
+			}
 		}
 		return;
 	}

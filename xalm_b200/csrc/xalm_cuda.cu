@@ -19,6 +19,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -67,6 +68,7 @@ static std::map<std::string, int>& tuning() {
 	    {"tma_rc", 0},       // 0 = auto, else force rows per tile (4 or 8)
 	    {"tma_ns_max", 4},   // most ring stages
 	    {"tma_ctas_per_sm", 2},
+	    {"tail_prefetch_mb", 8}, // each decode kernel pulls this many MB of the NEXT kernel's first weights into L2 once its own loads are issued
 	    {"prefill_split", 3}, // batched prefill operand precision: 1 = fp16 x fp16 (fastest; logits drift ~4e-2 over 32 layers), 2 = hi+lo fp16
 	                          // activations, 3 = hi+lo on activations, weights and attention operands (default: logits within ~1e-3 of the decode path)
 	};
@@ -1133,6 +1135,18 @@ static int enqueue_token(xalm_cuda_model* m, int mode, cudaStream_t s, int* n_la
 		AttnArgs a_at;
 		fill_layer_args(m, l, &a_qkv, &a_at, &a_wo, &a_w13, &a_w2);
 		(void) L;
+		if (const int pf_mb = tune("tail_prefetch_mb")) { // chain: every kernel warms L2 with the head of the next kernel's stream
+			auto head = [&](const WMat& w, const uint8_t** ptr, unsigned long long* bytes) {
+				*ptr = w.p0;
+				*bytes = std::min<unsigned long long>((unsigned long long) w.s0 * w.rows, (unsigned long long) pf_mb << 20);
+			};
+			a_qkv.pf_kv = 1;
+			head(a_wo.w, &a_at.pf_ptr, &a_at.pf_bytes);
+			head(a_w13.w, &a_wo.pf_ptr, &a_wo.pf_bytes);
+			head(a_w2.w, &a_w13.pf_ptr, &a_w13.pf_bytes);
+			if (l + 1 < c.n_layers) head(m->layers[l + 1].wqkv.m, &a_w2.pf_ptr, &a_w2.pf_bytes);
+			else if (mode == XALM_OUTPUT_LOGITS) head(m->wcls.m, &a_w2.pf_ptr, &a_w2.pf_bytes);
+		}
 		{ // attention pre-norm + q,k,v + clip + rope + KV write (+ sinks)
 			XALM_TRY(launch_matvec(a_qkv, s, pdl));
 			nl++;
