@@ -203,6 +203,38 @@ def gemm_flops(cfg: dict, T: int, with_cls: bool = True) -> float:
     return 2.0 * T * (cfg["n_layers"] * per_layer + (cfg["vocab_size"] * cfg["dim"] if with_cls else 0))
 
 
+def perplexity_summary(model, cfg, capi, n_tok: int) -> dict:
+    """Device-timed tok/s of the batched perplexity pass (BASELINE config[2]) in both operand modes + its accuracy against
+    the decode kernels, on the model bench.py already holds.  Full line: `bench.py --workload perplexity`."""
+    import torch
+    from xalm_b200.model import InferenceState
+    rng = np.random.default_rng(321)
+    toks = rng.integers(3, cfg["vocab_size"], size=n_tok + 1).astype(np.int32)
+    out = {"tokens_per_step": n_tok, "metric": "perplexity_tokens_per_s"}
+    st = InferenceState(cfg).cuda()
+    for split, name in ((3, "precise_hi_lo_fp16"), (1, "plain_fp16")):
+        capi.tune("prefill_split", split)
+        for _ in range(2):
+            model.prefill_async(toks[:-1], 0, 2)
+        model.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            model.prefill_async(toks[:-1], 0, 2)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        lg_all, probs = model.prefill(toks[:-1], 0, want_logits=2, targets=toks[1:])
+        worst = 0.0
+        for pos in range(n_tok - 2, n_tok):
+            model.forward(st, int(toks[pos]), pos, 1)
+            worst = max(worst, float(np.max(np.abs(st.logits() - lg_all[pos]))))
+        out[name] = {"value": n_tok / (ms / 1e3), "unit": "tok/s", "ms_per_step": ms, "gemm_tflops": gemm_flops(cfg, n_tok) / (ms / 1e3) / 1e12,
+                     "max_abs_logit_diff_vs_decode_path": worst, "perplexity": float(np.exp(-np.mean(np.log(probs))))}
+    capi.tune("prefill_split", 3)
+    return out
+
+
 def run_perplexity_workload(args):
     """BASELINE config[2]: perplexity mode on a 4k-token synthetic input.  A step = one batched pass over `--tokens` positions
     (every position's logits + softmax-at-target), weights resident.  `value` device-timed; `e2e` through Model.prefill with
@@ -342,6 +374,7 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-tokens", type=int, default=6, help="tokens the CPU baseline decodes (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-prefill", action="store_true", help="skip the perplexity-mode summary appended to the decode line at N=1")
     ap.add_argument("--workload", default="decode", choices=["decode", "perplexity"],
                     help="decode = BASELINE config[1] (the headline metric); perplexity = config[2]: batched prefill of a 4k-token input")
     ap.add_argument("--tokens", type=int, default=4096, help="perplexity workload: tokens per step")
@@ -475,6 +508,13 @@ def main():
                           "frac_of_8000": step_gbs / 8000.0, "formula": "Model::active_bytes(pos) (model.cpp:12-35), mean over the timed positions"},
         "notes": f"weights generated+uploaded in {gen_s:.0f}s; host cores {os.cpu_count()}",
     }
+
+    # ---- BASELINE config[2] beside it (N = 1): the batched prefill / perplexity pass on the same resident model ----
+    if world == 1 and not args.no_prefill and cfg["head_dim"] in (64, 128):
+        try:
+            line["perplexity_mode"] = perplexity_summary(model, cfg, capi, min(4096, ctx))
+        except Exception as ex:  # never lose the decode line to the secondary measurement
+            line["perplexity_mode"] = {"error": str(ex)[:200]}
 
     # ---- CPU baseline beside it: the oracle port on the host cores, same weights (rank 0, N = 1 only) ----
     if keep_host:
