@@ -55,6 +55,17 @@ struct MatvecArgs {
 	const uint8_t* pf_ptr;       // next kernel's weights (or nullptr)
 	unsigned long long pf_bytes;
 	int pf_kv;                   // 1: also prefetch rows [0, kv_len) of k_cache / v_cache (the attention kernel that follows QKV)
+	// tensor-parallel exchange fused into the matvec kernels (matvec_tma.cuh), LL style: the row-split matvecs (Wo, W2) PUSH every
+	// partial row as an 8-byte {value, sequence tag} word straight into every rank's receive slot over NVLink (posted stores, no
+	// fence, no flag, no extra kernel); the next kernel's rmsnorm prologue polls the tags of the words it needs and adds the
+	// partials (fixed rank order) to the residual stream.
+	uint2* push_dst[8];          // per destination rank: its receive slot for THIS rank's partial, (dim,) {float bits, tag}
+	int n_push;                  // 0 = off
+	int push_idx;                // exchange index inside the token: tag = step->ar_base + push_idx + 1
+	const uint2* recv;           // local receive slot: (n_recv, dim) words
+	int n_recv;                  // 0 = off
+	int recv_idx;
+	float* x_out;                // CTA 0 stores x + sum(partials) here: the residual stream after the exchange
 	// L2 prefetcher hand-shake (prefetch.cuh): block 0 publishes "kernel #prog_idx of this token has started"
 	unsigned int* progress;
 	int prog_idx;

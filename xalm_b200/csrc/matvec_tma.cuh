@@ -294,7 +294,22 @@ __global__ void __launch_bounds__((TMA_NW + 1) * 32, 1) matvec_tma_kernel(const 
 		};
 		float ss = 0.f;
 		for (int i = threadIdx.x * 4; i < a.n; i += TMA_NW * 32 * 4) {
-			const float4 v = ld_act4(a.x + i);
+			float4 v = ld_act4(a.x + i);
+			if (NORM && a.n_recv) { // x += sum over ranks (rank order: identical bits on every rank), infer.cpp:450-452 / :492-494
+				const unsigned int seq = a.step->ar_base + (unsigned int) a.recv_idx + 1u;
+				float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+				for (int p = 0; p < a.n_recv; p++) {
+					const uint2* src = a.recv + (size_t) p * a.n + i; // four {value, tag} words; poll until all four carry this exchange's tag
+					uint4 w0, w1;
+					do {
+						asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w0.x), "=r"(w0.y), "=r"(w0.z), "=r"(w0.w) : "l"(src));
+						asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w1.x), "=r"(w1.y), "=r"(w1.z), "=r"(w1.w) : "l"(src + 2));
+					} while (w0.y != seq || w0.w != seq || w1.y != seq || w1.w != seq);
+					sum.x += __uint_as_float(w0.x); sum.y += __uint_as_float(w0.z); sum.z += __uint_as_float(w1.x); sum.w += __uint_as_float(w1.z);
+				}
+				v.x += sum.x; v.y += sum.y; v.z += sum.z; v.w += sum.w;
+				if (blockIdx.x == 0) *reinterpret_cast<float4*>(a.x_out + i) = v;
+			}
 			*reinterpret_cast<float4*>(xb + xpos(i)) = v;
 			ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
 		}
@@ -391,6 +406,12 @@ __global__ void __launch_bounds__((TMA_NW + 1) * 32, 1) matvec_tma_kernel(const 
 			const int row0 = ((int) blockIdx.x + tt * (int) gridDim.x) * RC;
 			if (a.epi == EPI_RESIDUAL) {
 				if (lane < RC && row0 + lane < a.d) a.out[row0 + lane] = xold + yv;
+			} else if (a.epi == EPI_STORE && a.n_push) { // tensor parallel: this rank's partial rows go to every rank (NVLink stores)
+				if (lane < RC && (lane & 1) == 0 && row0 + lane < a.d) {
+					const unsigned int seq = a.step->ar_base + (unsigned int) a.push_idx + 1u;
+					const uint4 w = make_uint4(__float_as_uint(yv), seq, __float_as_uint(ynext), seq);
+					for (int p = 0; p < a.n_push; p++) *reinterpret_cast<uint4*>(a.push_dst[p] + row0 + lane) = w;
+				}
 			} else if (lane < RC && (lane & 1) == 0 && a.epi != EPI_GLU) { // GLU below (partner rows RC/2 apart)
 				const float y2[2] = {yv, ynext};
 				epilogue<2>(a, row0 + lane, y2);

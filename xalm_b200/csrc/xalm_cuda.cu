@@ -68,6 +68,7 @@ static std::map<std::string, int>& tuning() {
 	    {"tma_rc", 0},       // 0 = auto, else force rows per tile (4 or 8)
 	    {"tma_ns_max", 4},   // most ring stages
 	    {"tma_ctas_per_sm", 2},
+	    {"tp_fused", 1},     // tensor parallel: fuse the two per-layer exchanges into the matvec kernels (push over NVLink + receive in the next prologue)
 	    {"tail_prefetch_mb", 8}, // each decode kernel pulls this many MB of the NEXT kernel's first weights into L2 once its own loads are issued
 	    {"prefill_split", 3}, // batched prefill operand precision: 1 = fp16 x fp16 (fastest; logits drift ~4e-2 over 32 layers), 2 = hi+lo fp16
 	                          // activations, 3 = hi+lo on activations, weights and attention operands (default: logits within ~1e-3 of the decode path)
@@ -297,6 +298,7 @@ static int launch_matvec(MatvecArgs a, cudaStream_t s, bool pdl) {
 		const int rc = launch_matvec_tma(a, s, pdl);
 		if (rc >= 0) return rc;
 	}
+	if (a.n_push || a.n_recv) return set_error(XALM_ERR_STATE, "fused tensor-parallel exchange needs the TMA matvec kernel (n=%d d=%d type=%d)", a.n, a.d, t);
 	if (t == XALM_TQ1_0) {
 		if (a.n % 256) return set_error(XALM_ERR_INVALID, "TQ1_0 rows must be a multiple of 256 elements (n=%d)", a.n);
 		dim3 grid((vrows + 4 * 4 - 1) / (4 * 4)), block(4 * 32);
@@ -370,6 +372,7 @@ struct PeerArgs {
 	float* data[8];          // exchange buffers of all ranks (peer-mapped), [2][stride] floats each
 	unsigned int* flags[8];  // flag arrays of all ranks, [2][8] u32 each
 	int rank, size, stride;
+	uint2* recv[8];          // per rank: its receive area [2 slots][8 source ranks][dim] of {value, tag} words (fused exchange, matvec_tma.cuh)
 };
 __global__ void peer_allreduce_residual_kernel(const PeerArgs pa, float* __restrict__ x, int n, int idx, const StepParams* step) {
 	pdl_launch_dependents();
@@ -668,6 +671,9 @@ struct xalm_cuda_model {
 	// peer-memory allreduce
 	float* xchg = nullptr;            // [2][dim] floats + [2][8] u32 flags, cudaMalloc'd (IPC-exportable)
 	bool peer_ready = false;
+	bool tp_fused = false;            // exchanges fused into the matvec kernels (push + receive in the next prologue)
+	float* x_alt = nullptr;           // second residual-stream buffer (the fused exchange ping-pongs x)
+	unsigned int* push_ticket = nullptr;
 	xalm::PeerArgs peer = {};
 	std::vector<void*> peer_opened;
 	unsigned int token_serial = 0;
@@ -813,7 +819,8 @@ int xalm_cuda_ipc_export(xalm_cuda_model* m, void* handle64) {
 	XALM_CUDA_CHECK(cudaSetDevice(m->device));
 	static_assert(sizeof(cudaIpcMemHandle_t) == XALM_IPC_HANDLE_BYTES, "cudaIpcMemHandle_t size");
 	if (!m->xchg) {
-		const size_t bytes = (size_t) 2 * m->c.dim * sizeof(float) + 2 * 8 * sizeof(unsigned int);
+		// [2][dim] pull slots | [2][8] flags | [2][8][dim] receive slots of 8-byte {value, tag} words
+		const size_t bytes = (size_t) (2 + 32) * m->c.dim * sizeof(float) + 2 * 8 * sizeof(unsigned int);
 		XALM_CUDA_CHECK(cudaMalloc((void**) &m->xchg, bytes)); // its own allocation: the IPC handle covers exactly this buffer
 		XALM_CUDA_CHECK(cudaMemset(m->xchg, 0, bytes));
 		XALM_CUDA_CHECK(cudaDeviceSynchronize());
@@ -844,6 +851,7 @@ int xalm_cuda_ipc_import(xalm_cuda_model* m, const void* handles) {
 		}
 		m->peer.data[p] = base;
 		m->peer.flags[p] = reinterpret_cast<unsigned int*>(base + data_floats);
+		m->peer.recv[p] = reinterpret_cast<uint2*>(base + data_floats + 16);
 	}
 	m->peer.rank = m->tp_rank; m->peer.size = m->tp_size; m->peer.stride = m->c.dim;
 	m->peer_ready = true;
@@ -1129,12 +1137,35 @@ static int enqueue_token(xalm_cuda_model* m, int mode, cudaStream_t s, int* n_la
 		if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "megakernel launch failed: %s", cudaGetErrorString(e));
 		nl++;
 	}
+	// fused tensor-parallel exchange: Wo / W2 push their partial rows to every rank, the next norm-prologue kernel receives
+	const bool fused = tp && m->peer_ready && m->tp_fused;
+	float* X[2] = {m->x, m->x_alt};
+	int cur = 0; // which buffer holds the residual stream
+	auto set_push = [&](MatvecArgs& a, int idx) {
+		const int slot = idx & 1;
+		a.epi = EPI_STORE; a.out = nullptr; a.step = m->d_step;
+		a.n_push = m->tp_size; a.push_idx = idx;
+		for (int p = 0; p < m->tp_size; p++) a.push_dst[p] = m->peer.recv[p] + (size_t) (slot * 8 + m->tp_rank) * c.dim;
+	};
+	auto set_recv = [&](MatvecArgs& a, int idx) {
+		const int slot = idx & 1;
+		a.step = m->d_step; a.n_recv = m->tp_size; a.recv_idx = idx;
+		a.recv = m->peer.recv[m->tp_rank] + (size_t) slot * 8 * c.dim;
+		a.x = X[cur]; a.x_out = X[cur ^ 1];
+		cur ^= 1;
+	};
 	for (int l = 0; l < c.n_layers && !m->mega; l++) {
 		LayerDev& L = m->layers[l];
 		MatvecArgs a_qkv, a_wo, a_w13, a_w2;
 		AttnArgs a_at;
 		fill_layer_args(m, l, &a_qkv, &a_at, &a_wo, &a_w13, &a_w2);
 		(void) L;
+		if (fused) {
+			if (l > 0) set_recv(a_qkv, 2 * l - 1);
+			set_push(a_wo, 2 * l);
+			set_recv(a_w13, 2 * l);
+			set_push(a_w2, 2 * l + 1);
+		}
 		if (const int pf_mb = tune("tail_prefetch_mb")) { // chain: every kernel warms L2 with the head of the next kernel's stream
 			auto head = [&](const WMat& w, const uint8_t** ptr, unsigned long long* bytes) {
 				*ptr = w.p0;
@@ -1157,10 +1188,11 @@ static int enqueue_token(xalm_cuda_model* m, int mode, cudaStream_t s, int* n_la
 		}
 		{ // Wo + residual
 			MatvecArgs a = a_wo;
-			if (tp && m->peer_ready) a.out = m->xchg + (size_t) ((2 * l) & 1) * c.dim;
+			if (tp && m->peer_ready && !fused) a.out = m->xchg + (size_t) ((2 * l) & 1) * c.dim;
 			XALM_TRY(launch_matvec(a, s, pdl));
 			nl++;
-			if (tp && m->peer_ready) {
+			if (fused) {
+			} else if (tp && m->peer_ready) {
 				e = launch(peer_allreduce_residual_kernel, dim3(4), dim3(256), s, pdl, m->peer, m->x, c.dim, 2 * l, (const StepParams*) m->d_step);
 				if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "peer allreduce launch failed: %s", cudaGetErrorString(e));
 				nl++;
@@ -1177,10 +1209,11 @@ static int enqueue_token(xalm_cuda_model* m, int mode, cudaStream_t s, int* n_la
 		}
 		{ // W2 + residual
 			MatvecArgs a = a_w2;
-			if (tp && m->peer_ready) a.out = m->xchg + (size_t) ((2 * l + 1) & 1) * c.dim;
+			if (tp && m->peer_ready && !fused) a.out = m->xchg + (size_t) ((2 * l + 1) & 1) * c.dim;
 			XALM_TRY(launch_matvec(a, s, pdl));
 			nl++;
-			if (tp && m->peer_ready) {
+			if (fused) {
+			} else if (tp && m->peer_ready) {
 				e = launch(peer_allreduce_residual_kernel, dim3(4), dim3(256), s, pdl, m->peer, m->x, c.dim, 2 * l + 1, (const StepParams*) m->d_step);
 				if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "peer allreduce launch failed: %s", cudaGetErrorString(e));
 				nl++;
@@ -1197,7 +1230,8 @@ static int enqueue_token(xalm_cuda_model* m, int mode, cudaStream_t s, int* n_la
 		a.w = m->wcls.m; a.x = m->x; a.n = c.dim; a.d = m->vocab_l; a.epi = EPI_STORE;
 		a.norm_w = m->rms_final; a.norm_type = m->rms_final_type; a.norm_eps = c.norm_eps; a.out = m->logits;
 		a.progress = m->d_progress; a.prog_idx = 4 * c.n_layers;
-		XALM_TRY(launch_matvec(a, s, pdl && !tp));
+		if (fused && c.n_layers > 0) set_recv(a, 2 * c.n_layers - 1);
+		XALM_TRY(launch_matvec(a, s, pdl && (!tp || fused)));
 		nl++;
 		if (tp) {
 			XALM_NCCL_CHECK(g_nccl.AllGather(m->logits, m->logits_full, m->vocab_l, ncclFloat32, m->comm, s));
@@ -1280,6 +1314,16 @@ int xalm_cuda_finalize(xalm_cuda_model* m) {
 	XALM_TRY(fzero(&m->q, m->q_dim_l));
 	XALM_TRY(fzero(&m->logits, m->vocab_l));
 	XALM_TRY(fzero(&m->part, c.dim));
+	XALM_TRY(fzero(&m->x_alt, c.dim));
+	XALM_TRY(m->da.alloc((void**) &m->push_ticket, 64));
+	XALM_CUDA_CHECK(cudaMemset(m->push_ticket, 0, 64));
+	if (m->tp_size > 1 && m->peer_ready && tune("tp_fused")) {
+		auto takes = [&](const WMat& w, int n) { return (w.layout_units || tma_eligible(w, n)) && w.rows % 8 == 0 && n % 256 == 0; };
+		bool ok = takes(m->wcls.m, c.dim) && (size_t) c.dim * sizeof(float) <= 64 * 1024;
+		for (auto& L : m->layers)
+			ok = ok && takes(L.wqkv.m, c.dim) && takes(L.wo.m, m->q_dim_l) && takes(L.w13.m, c.dim) && takes(L.w2.m, m->hidden_l);
+		m->tp_fused = ok;
+	}
 	if (m->tp_size > 1) XALM_TRY(fzero(&m->logits_full, c.vocab_size));
 	else m->logits_full = m->logits;
 	const size_t kv_elems = (size_t) c.max_seq_len * m->kv_dim_l;

@@ -33,6 +33,9 @@ SHAPES = {
     # small shapes for tests / smoke
     "tiny": dict(dim=256, hidden_dim=512, head_dim=64, n_layers=2, n_heads=4, n_kv_heads=2, vocab_size=512,
                  max_seq_len=128, rope_theta=10000.0, arch="MistralForCausalLM"),
+    # every per-rank dimension stays a multiple of 256 up to TP=4 (the fused exchange rides on the TMA matvec kernels)
+    "tp": dict(dim=1024, hidden_dim=3072, head_dim=128, n_layers=4, n_heads=8, n_kv_heads=4, vocab_size=4096,
+               max_seq_len=1024, rope_theta=10000.0, arch="LlamaForCausalLM"),
     "small": dict(dim=1024, hidden_dim=2816, head_dim=128, n_layers=4, n_heads=8, n_kv_heads=2, vocab_size=4096,
                   max_seq_len=1024, rope_theta=10000.0, arch="LlamaForCausalLM"),
 }
