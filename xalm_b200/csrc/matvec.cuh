@@ -65,7 +65,8 @@ struct MatvecArgs {
 	const uint2* recv;           // local receive slot: (n_recv, dim) words
 	int n_recv;                  // 0 = off
 	int recv_idx;
-	float* x_out;                // CTA 0 stores x + sum(partials) here: the residual stream after the exchange
+	float* x_out;                // the first CTAs store x + sum(partials) here: the residual stream after the exchange
+	uint2* xl;                   // local (dim,) {value, tag} words: the reducing CTAs publish the summed stream here, every CTA polls it
 	// L2 prefetcher hand-shake (prefetch.cuh): block 0 publishes "kernel #prog_idx of this token has started"
 	unsigned int* progress;
 	int prog_idx;

@@ -283,6 +283,34 @@ __global__ void __launch_bounds__((TMA_NW + 1) * 32, 1) matvec_tma_kernel(const 
 			*kp = __floats2half2_rn(v.x, v.y);
 		}
 	}
+	// ---- tensor-parallel receive (LL style): the first CTAs each reduce a slice of the stream — x += sum over ranks of the partial
+	//      rows the previous row-split matvec pushed here (rank order: identical bits on every rank; infer.cpp:450-452 / :492-494) —
+	//      and publish it locally as {value, tag} words, so every other CTA reads dim words instead of n_ranks x dim ----
+	if (NORM && a.n_recv) {
+		const int n_red = min((int) gridDim.x, 8);
+		if ((int) blockIdx.x < n_red) {
+			const unsigned int seq = a.step->ar_base + (unsigned int) a.recv_idx + 1u;
+			const int chunk = ((a.n / 4 + n_red - 1) / n_red) * 4;
+			const int i0 = (int) blockIdx.x * chunk, i1 = min(a.n, i0 + chunk);
+			for (int i = i0 + (int) threadIdx.x * 4; i < i1; i += TMA_NW * 32 * 4) {
+				float4 v = ld_act4(a.x + i);
+				float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+				for (int p = 0; p < a.n_recv; p++) {
+					const uint2* src = a.recv + (size_t) p * a.n + i; // four {value, tag} words; poll until all carry this exchange's tag
+					uint4 w0, w1;
+					do {
+						asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w0.x), "=r"(w0.y), "=r"(w0.z), "=r"(w0.w) : "l"(src));
+						asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w1.x), "=r"(w1.y), "=r"(w1.z), "=r"(w1.w) : "l"(src + 2));
+					} while (w0.y != seq || w0.w != seq || w1.y != seq || w1.w != seq);
+					sum.x += __uint_as_float(w0.x); sum.y += __uint_as_float(w0.z); sum.z += __uint_as_float(w1.x); sum.w += __uint_as_float(w1.z);
+				}
+				v.x += sum.x; v.y += sum.y; v.z += sum.z; v.w += sum.w;
+				*reinterpret_cast<float4*>(a.x_out + i) = v;
+				*reinterpret_cast<uint4*>(a.xl + i) = make_uint4(__float_as_uint(v.x), seq, __float_as_uint(v.y), seq);
+				*reinterpret_cast<uint4*>(a.xl + i + 2) = make_uint4(__float_as_uint(v.z), seq, __float_as_uint(v.w), seq);
+			}
+		}
+	}
 	// ---- stage activations: xb = NORM ? x * scale * g : x ----
 	if (!xg) {
 		// xb is stored permuted inside each 256-element unit: the E floats a lane needs for one piece are split into
@@ -294,21 +322,18 @@ __global__ void __launch_bounds__((TMA_NW + 1) * 32, 1) matvec_tma_kernel(const 
 		};
 		float ss = 0.f;
 		for (int i = threadIdx.x * 4; i < a.n; i += TMA_NW * 32 * 4) {
-			float4 v = ld_act4(a.x + i);
-			if (NORM && a.n_recv) { // x += sum over ranks (rank order: identical bits on every rank), infer.cpp:450-452 / :492-494
+			float4 v;
+			if (NORM && a.n_recv) { // the summed stream, published by the reducing CTAs below as {value, tag} words: poll this exchange's tag
 				const unsigned int seq = a.step->ar_base + (unsigned int) a.recv_idx + 1u;
-				float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
-				for (int p = 0; p < a.n_recv; p++) {
-					const uint2* src = a.recv + (size_t) p * a.n + i; // four {value, tag} words; poll until all four carry this exchange's tag
-					uint4 w0, w1;
-					do {
-						asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w0.x), "=r"(w0.y), "=r"(w0.z), "=r"(w0.w) : "l"(src));
-						asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w1.x), "=r"(w1.y), "=r"(w1.z), "=r"(w1.w) : "l"(src + 2));
-					} while (w0.y != seq || w0.w != seq || w1.y != seq || w1.w != seq);
-					sum.x += __uint_as_float(w0.x); sum.y += __uint_as_float(w0.z); sum.z += __uint_as_float(w1.x); sum.w += __uint_as_float(w1.z);
-				}
-				v.x += sum.x; v.y += sum.y; v.z += sum.z; v.w += sum.w;
-				if (blockIdx.x == 0) *reinterpret_cast<float4*>(a.x_out + i) = v;
+				const uint2* src = a.xl + i;
+				uint4 w0, w1;
+				do {
+					asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w0.x), "=r"(w0.y), "=r"(w0.z), "=r"(w0.w) : "l"(src));
+					asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w1.x), "=r"(w1.y), "=r"(w1.z), "=r"(w1.w) : "l"(src + 2));
+				} while (w0.y != seq || w0.w != seq || w1.y != seq || w1.w != seq);
+				v = make_float4(__uint_as_float(w0.x), __uint_as_float(w0.z), __uint_as_float(w1.x), __uint_as_float(w1.z));
+			} else {
+				v = ld_act4(a.x + i);
 			}
 			*reinterpret_cast<float4*>(xb + xpos(i)) = v;
 			ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;

@@ -673,7 +673,7 @@ struct xalm_cuda_model {
 	bool peer_ready = false;
 	bool tp_fused = false;            // exchanges fused into the matvec kernels (push + receive in the next prologue)
 	float* x_alt = nullptr;           // second residual-stream buffer (the fused exchange ping-pongs x)
-	unsigned int* push_ticket = nullptr;
+	uint2* xl = nullptr;              // [2][dim] {value, tag} words: the summed stream published inside a receiving kernel
 	xalm::PeerArgs peer = {};
 	std::vector<void*> peer_opened;
 	unsigned int token_serial = 0;
@@ -1151,6 +1151,7 @@ static int enqueue_token(xalm_cuda_model* m, int mode, cudaStream_t s, int* n_la
 		const int slot = idx & 1;
 		a.step = m->d_step; a.n_recv = m->tp_size; a.recv_idx = idx;
 		a.recv = m->peer.recv[m->tp_rank] + (size_t) slot * 8 * c.dim;
+		a.xl = m->xl + (size_t) slot * c.dim;
 		a.x = X[cur]; a.x_out = X[cur ^ 1];
 		cur ^= 1;
 	};
@@ -1315,8 +1316,8 @@ int xalm_cuda_finalize(xalm_cuda_model* m) {
 	XALM_TRY(fzero(&m->logits, m->vocab_l));
 	XALM_TRY(fzero(&m->part, c.dim));
 	XALM_TRY(fzero(&m->x_alt, c.dim));
-	XALM_TRY(m->da.alloc((void**) &m->push_ticket, 64));
-	XALM_CUDA_CHECK(cudaMemset(m->push_ticket, 0, 64));
+	XALM_TRY(m->da.alloc((void**) &m->xl, (size_t) 2 * c.dim * sizeof(uint2)));
+	XALM_CUDA_CHECK(cudaMemset(m->xl, 0, (size_t) 2 * c.dim * sizeof(uint2)));
 	if (m->tp_size > 1 && m->peer_ready && tune("tp_fused")) {
 		auto takes = [&](const WMat& w, int n) { return (w.layout_units || tma_eligible(w, n)) && w.rows % 8 == 0 && n % 256 == 0; };
 		bool ok = takes(m->wcls.m, c.dim) && (size_t) c.dim * sizeof(float) <= 64 * 1024;
