@@ -140,3 +140,27 @@ def test_perplexity_probabilities():
     ppl_ref, ppl = np.exp(-np.mean(ref_lp)), np.exp(-np.mean(lp))
     assert abs(ppl - ppl_ref) <= 2e-3 * ppl_ref
     gm.close(); om.close()
+
+
+def test_prefill_gelu_tied_embeddings_partial_rotary():
+    """The config switches of model.h:44-90 through the batched path: gelu GLU, classifier tied to the embedding, rotary_dim < head_dim."""
+    config, om, gm = synth_pair("tiny", "f16", seed=8, std=0.06, act_type="gelu", tie_word_embeddings=True, rotary_dim=32)
+    tokens = np.random.default_rng(5).integers(3, config["vocab_size"], size=90).astype(np.int32)
+    ref = _oracle_all_logits(om, tokens)
+    got = gm.prefill(tokens, 0, want_logits=2)
+    assert np.max(np.abs(got - ref)) <= 1e-3
+    gm.close(); om.close()
+
+
+def test_prefill_single_token_and_full_cache():
+    """Edge sizes: one position; a batch that fills the KV cache exactly (max_seq_len = 128 for the tiny shape)."""
+    config, om, gm = synth_pair("tiny", "q8_0", seed=13, std=0.06)
+    tokens = np.random.default_rng(6).integers(3, config["vocab_size"], size=config["max_seq_len"]).astype(np.int32)
+    ref = _oracle_all_logits(om, tokens)
+    one = gm.prefill(tokens[:1], 0, want_logits=1)
+    assert np.max(np.abs(one - ref[0])) <= 1e-3
+    got = gm.prefill(tokens, 0, want_logits=2)
+    assert np.max(np.abs(got - ref)) <= 1e-3
+    with pytest.raises(capi.XalmError):
+        gm.prefill(tokens[:2], config["max_seq_len"] - 1, want_logits=0)
+    gm.close(); om.close()

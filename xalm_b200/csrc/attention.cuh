@@ -240,6 +240,16 @@ __global__ void __launch_bounds__(NW * 32) attn_decode_kernel(const AttnArgs a) 
 	__threadfence();
 	const float* bacc = a.part_acc + (size_t) kvh * a.n_splits * G * HD;
 	const float* bml = a.part_ml + (size_t) kvh * a.n_splits * G * 2;
+	// every partial of this thread's first four outputs is requested BEFORE the scales are computed: one L2 round trip for up
+	// to 16 splits, overlapped with the (m, l) pass, instead of a chain of dependent ones after it
+	constexpr int MB = 16;
+	float4 pv[MB];
+	auto preload = [&](int i4, int s0) {
+#pragma unroll
+		for (int k = 0; k < MB; k++)
+			if (s0 + k < n_active) pv[k] = __ldcg(reinterpret_cast<const float4*>(bacc + (size_t) (s0 + k) * G * HD + i4));
+	};
+	if ((int) threadIdx.x * 4 < G * HD) preload((int) threadIdx.x * 4, 0);
 	// (m, l) of every split -> shared memory (reusing s_acc), then per-head max, rescale factors and denominators
 	float* s_ml = &s_acc[0][0][0];                 // [n_active][G][2]   (n_active * G * 2 <= NW * G * HD)
 	float* s_sc = s_ml + (size_t) n_active * G * 2; // [n_active][G]
@@ -259,19 +269,21 @@ __global__ void __launch_bounds__(NW * 32) attn_decode_kernel(const AttnArgs a) 
 		s_den[g] = den;
 	}
 	__syncthreads();
-	for (int i = threadIdx.x; i < G * HD; i += NW * 32) {
-		const int g = i / HD;
-		float num = 0.f;
-		int sidx = 0;
-		for (; sidx + 8 <= n_active; sidx += 8) { // 8 independent L2 loads in flight per thread
-			float v[8];
+	for (int i4 = threadIdx.x * 4; i4 < G * HD; i4 += NW * 32 * 4) {
+		const int g = i4 / HD;
+		float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
+		for (int s0 = 0; s0 < n_active; s0 += MB) {
+			if (s0 > 0 || i4 != (int) threadIdx.x * 4) preload(i4, s0); // the first batch is already in flight
 #pragma unroll
-			for (int k = 0; k < 8; k++) v[k] = __ldcg(bacc + (size_t) (sidx + k) * G * HD + i);
-#pragma unroll
-			for (int k = 0; k < 8; k++) num += s_sc[(sidx + k) * G + g] * v[k];
+			for (int k = 0; k < MB; k++) {
+				if (s0 + k < n_active) {
+					const float sc = s_sc[(s0 + k) * G + g];
+					num.x += sc * pv[k].x; num.y += sc * pv[k].y; num.z += sc * pv[k].z; num.w += sc * pv[k].w;
+				}
+			}
 		}
-		for (; sidx < n_active; sidx++) num += s_sc[sidx * G + g] * __ldcg(bacc + (size_t) sidx * G * HD + i);
-		a.out[(size_t) kvh * G * HD + i] = num / s_den[g];
+		const float den = s_den[g];
+		*reinterpret_cast<float4*>(a.out + (size_t) kvh * G * HD + i4) = make_float4(num.x / den, num.y / den, num.z / den, num.w / den);
 	}
 }
 

@@ -629,31 +629,44 @@ __global__ void rope_table_kernel(const float* __restrict__ freq, int half_dim, 
 	}
 }
 
-// rmsnorm (infer.cpp:224-236) of each row, result as an A-tile operand.  One warp per row, the row held in registers.
-__global__ void rmsnorm_rows_kernel(const float* __restrict__ x, int T, int dim, const uint8_t* __restrict__ w, int wtype, float eps, ATiles o) {
-	const int warps = blockDim.x >> 5;
-	const int lane = threadIdx.x & 31;
-	constexpr int MAXC = 16; // 8-element chunks per lane kept in registers (rows up to 4096 elements); longer rows re-read the tail
-	for (int m = blockIdx.x * warps + (threadIdx.x >> 5); m < T; m += gridDim.x * warps) {
+// rmsnorm (infer.cpp:224-236) of each row, result as an A-tile operand.  One 128-thread CTA per row: the row stays in registers
+// (up to 8 chunks of 8 floats per thread = 8192 elements; longer rows re-read), the norm weights are requested before the
+// block reduction so both loads overlap.
+__global__ void __launch_bounds__(128) rmsnorm_rows_kernel(const float* __restrict__ x, int T, int dim, const uint8_t* __restrict__ w, int wtype, float eps,
+                                                           ATiles o) {
+	__shared__ float red[4];
+	constexpr int MAXC = 8;
+	const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+	for (int m = blockIdx.x; m < T; m += gridDim.x) {
 		const float* xr = x + (size_t) m * dim;
 		float4 buf[MAXC][2];
 		float ss = 0.f;
 #pragma unroll
 		for (int c = 0; c < MAXC; c++) {
-			const int j = lane * 8 + c * 256;
+			const int j = threadIdx.x * 8 + c * 1024;
 			if (j < dim) {
 				buf[c][0] = *reinterpret_cast<const float4*>(xr + j);
 				buf[c][1] = *reinterpret_cast<const float4*>(xr + j + 4);
+			}
+		}
+#pragma unroll
+		for (int c = 0; c < MAXC; c++) {
+			const int j = threadIdx.x * 8 + c * 1024;
+			if (j < dim) {
 				const float4 a = buf[c][0], b = buf[c][1];
 				ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
 			}
 		}
-		for (int j = lane * 8 + MAXC * 256; j < dim; j += 256) {
+		for (int j = threadIdx.x * 8 + MAXC * 1024; j < dim; j += 1024) {
 			const float4 a = *reinterpret_cast<const float4*>(xr + j), b = *reinterpret_cast<const float4*>(xr + j + 4);
 			ss += a.x * a.x + a.y * a.y + a.z * a.z + a.w * a.w + b.x * b.x + b.y * b.y + b.z * b.z + b.w * b.w;
 		}
 		ss = warp_sum(ss);
-		const float scale = 1.0f / sqrtf(ss / (float) dim + eps);
+		__syncthreads(); // red[] of the previous row has been read by everyone
+		if (lane == 0) red[warp] = ss;
+		__syncthreads();
+		const float tot = red[0] + red[1] + red[2] + red[3];
+		const float scale = 1.0f / sqrtf(tot / (float) dim + eps);
 		auto emit = [&](int j, const float4& a, const float4& b) {
 			const float xv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
 			float gw[8];
@@ -674,10 +687,10 @@ __global__ void rmsnorm_rows_kernel(const float* __restrict__ x, int T, int dim,
 		};
 #pragma unroll
 		for (int c = 0; c < MAXC; c++) {
-			const int j = lane * 8 + c * 256;
+			const int j = threadIdx.x * 8 + c * 1024;
 			if (j < dim) emit(j, buf[c][0], buf[c][1]);
 		}
-		for (int j = lane * 8 + MAXC * 256; j < dim; j += 256)
+		for (int j = threadIdx.x * 8 + MAXC * 1024; j < dim; j += 1024)
 			emit(j, *reinterpret_cast<const float4*>(xr + j), *reinterpret_cast<const float4*>(xr + j + 4));
 	}
 }
@@ -1097,11 +1110,14 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const AttnTcArg
 		const int r = quad * 32 + lane; // query row inside the tile = TMEM lane
 		const int row = q0 + r;
 		const uint32_t lane_addr = (uint32_t) (quad * 32) << 16;
-		const float scale = 1.0f / sqrtf(128.0f);
+		// softmax in the log2 domain on the RAW scores: p = 2^(s*c1 - m*c1), c1 = log2(e)/sqrt(head_dim) -> one FFMA + one MUFU per
+		// element (ex2.approx: 2^-22 relative, far below the fp16 rounding of P even as a hi+lo pair)
+		const float c1 = 1.4426950408889634f / sqrtf(128.0f);
+		auto ex2 = [](float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; };
 		// The output accumulates in TMEM (PV with accumulate); it is rescaled only when a row's maximum grows by more than TAU
-		// over the maximum its probabilities are currently expressed against (exp(TAU) = 2981 still fits fp16 comfortably).
-		constexpr float TAU = 8.0f;
-		float m_run = -INFINITY, l_run = 0.f;
+		// (in natural-log units: exp(8) = 2981 still fits fp16 comfortably) over the maximum its probabilities are expressed against.
+		const float TAU_RAW = 8.0f * sqrtf(128.0f);
+		float m_run = -INFINITY, l_run = 0.f; // m_run: maximum of the raw scores
 		for (int j = 0; j < n_kb; j++) {
 			const int b = j & 1;
 			mb_wait(&s_full[b], (j >> 1) & 1);
@@ -1114,19 +1130,22 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const AttnTcArg
 			for (int c = 0; c < 4; c++) tmem_ld32_issue(TM_S0 + lane_addr + 128 * b + 32 * c, sv + 32 * c);
 			tmem_wait_ld();
 			float mx = -INFINITY;
+			if (need_mask) {
 #pragma unroll
-			for (int i = 0; i < 128; i++) {
-				float t = sv[i] * scale;
-				if (need_mask && i > lim) t = -INFINITY;
-				sv[i] = t;
-				mx = fmaxf(mx, t);
+				for (int i = 0; i < 128; i++) {
+					if (i > lim) sv[i] = -INFINITY;
+					mx = fmaxf(mx, sv[i]);
+				}
+			} else {
+#pragma unroll
+				for (int i = 0; i < 128; i++) mx = fmaxf(mx, sv[i]);
 			}
 			if (j > 0) mb_wait(o_full, (j - 1) & 1); // P V of the previous block has completed: the P tile is free, O is quiescent
-			const bool grow = mx > m_run + TAU;       // block 0: m_run = -inf -> true, but there is nothing to rescale yet
+			const bool grow = mx > m_run + TAU_RAW;   // block 0: m_run = -inf -> true, but there is nothing to rescale yet
 			if (j == 0) m_run = mx;
 			else if (__any_sync(0xffffffffu, grow)) {
 				const float m_new = grow ? mx : m_run;
-				const float corr = __expf(m_run - m_new); // 1 for the rows that keep their maximum
+				const float corr = ex2((m_run - m_new) * c1); // 1 for the rows that keep their maximum
 				tc_fence_after();
 #pragma unroll
 				for (int c = 0; c < 4; c++) {
@@ -1140,6 +1159,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const AttnTcArg
 				l_run *= corr;
 				m_run = m_new;
 			}
+			const float nm = -m_run * c1;
 			// ---- probabilities -> fp16 operand tile (hi, lo), row sum ----
 			float rs = 0.f;
 #pragma unroll
@@ -1147,7 +1167,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const AttnTcArg
 				__half2 hh[4], ll[4];
 #pragma unroll
 				for (int i = 0; i < 4; i++) {
-					const float p0 = __expf(sv[8 * g8 + 2 * i] - m_run), p1 = __expf(sv[8 * g8 + 2 * i + 1] - m_run);
+					const float p0 = ex2(fmaf(sv[8 * g8 + 2 * i], c1, nm)), p1 = ex2(fmaf(sv[8 * g8 + 2 * i + 1], c1, nm));
 					rs += p0 + p1;
 					hh[i] = __floats2half2_rn(p0, p1);
 					if (PRECISE) {
@@ -1460,14 +1480,14 @@ int prefill_run(const PrefillModel& pm, PrefillScratch** scratch, const int* tok
 	rope_table_kernel<<<std::min(cdiv(T * (c.head_dim / 2), 256), sm_count() * 8), 256, 0, s>>>(pm.rope_freq, c.head_dim / 2, T, pos0,
 	                                                                                             reinterpret_cast<float2*>(sc.rope.p));
 	launches += 2;
-	const int norm_grid = std::min(cdiv(T, 8), sm_count() * 8);
+	const int norm_grid = std::min(T, sm_count() * 16);
 	if (L) XALM_TRY(prep_qkv(0));
 	for (size_t l = 0; l < L; l++) {
 		const PrefillLayer& P = pm.layers[l];
 		if (!prefill_type_ok(P.wqkv.type)) return set_error(XALM_ERR_UNSUPPORTED, "prefill: weight type %d", P.wqkv.type);
 		// ---- attention half ----
 		t_begin("rmsnorm");
-		rmsnorm_rows_kernel<<<norm_grid, 256, 0, s>>>(x, T, c.dim, P.rms_att, P.rms_att_type, c.norm_eps, xb);
+		rmsnorm_rows_kernel<<<norm_grid, 128, 0, s>>>(x, T, c.dim, P.rms_att, P.rms_att_type, c.norm_eps, xb);
 		t_end();
 		XALM_TRY(prep(P.wo, false, 0, c.dim, pm.q_dim, NT_dim, KT_q));
 		GemmArgs g = {};
@@ -1496,7 +1516,7 @@ int prefill_run(const PrefillModel& pm, PrefillScratch** scratch, const int* tok
 		XALM_TRY(run(g, P.wo));
 		// ---- feed-forward half ----
 		t_begin("rmsnorm");
-		rmsnorm_rows_kernel<<<norm_grid, 256, 0, s>>>(x, T, c.dim, P.rms_ffn, P.rms_ffn_type, c.norm_eps, xb);
+		rmsnorm_rows_kernel<<<norm_grid, 128, 0, s>>>(x, T, c.dim, P.rms_ffn, P.rms_ffn_type, c.norm_eps, xb);
 		t_end();
 		XALM_TRY(prep(P.w2, false, 0, c.dim, c.hidden_dim, NT_dim, KT_h));
 		g = {};
@@ -1513,7 +1533,7 @@ int prefill_run(const PrefillModel& pm, PrefillScratch** scratch, const int* tok
 	}
 	if (want_logits) {
 		if (!L) XALM_TRY(prep(pm.wcls, false, 0, c.vocab_size, c.dim, NT_cls, KT_dim));
-		rmsnorm_rows_kernel<<<norm_grid, 256, 0, s>>>(x, T, c.dim, pm.rms_final, pm.rms_final_type, c.norm_eps, xb);
+		rmsnorm_rows_kernel<<<norm_grid, 128, 0, s>>>(x, T, c.dim, pm.rms_final, pm.rms_final_type, c.norm_eps, xb);
 		GemmArgs g = {};
 		g.a_hi = xb.hi; g.a_lo = xb.lo;
 		g.NT = NT_cls; g.KT = KT_dim; g.M = T; g.N = c.vocab_size; g.epi = GEPI_STORE;
