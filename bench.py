@@ -470,6 +470,14 @@ def main():
             tok = sampler.sample_argmax(state)
         barrier()
         e2e_s = time.perf_counter() - t0
+        # same loop with the sampler on the device: 4 bytes back per token instead of the logits
+        tok = toks[0]
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            tok = model.forward_argmax(tok, pos_list[i])
+        barrier()
+        e2e_dev_s = time.perf_counter() - t0
     if world > 1:
         t = torch.tensor([ms, e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -498,7 +506,9 @@ def main():
         "metric": "decode_tokens_per_s", "value": tps, "unit": "tok/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic", "config": workload_config(args, cfg),
-        "e2e": {"value": e2e_tps, "unit": "tok/s", "h2d_bytes_per_step": 32, "d2h_bytes_per_step": cfg["vocab_size"] * 4},
+        "e2e": {"value": e2e_tps, "unit": "tok/s", "h2d_bytes_per_step": 32, "d2h_bytes_per_step": cfg["vocab_size"] * 4,
+                "device_sampler": {"value": args.steps / e2e_dev_s, "unit": "tok/s", "d2h_bytes_per_step": 4,
+                                   "api": "xalm_cuda_forward_argmax (Sampler::sample_argmax on the device)"}},
         "gpu_launches": launches,
         "clocks": clocks.summary(),
         "roofline": {"bound": "hbm", "achieved": k_gbs, "peak": peak, "unit": "GB/s", "frac": k_gbs / peak, "traffic": traffic,

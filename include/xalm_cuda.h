@@ -111,6 +111,9 @@ int xalm_cuda_set_stream(xalm_cuda_model* m, void* cuda_stream);
 /* Synchronous: on return with mode == XALM_OUTPUT_LOGITS, `logits_host` (vocab_size floats, caller-owned,
  * may be pageable) holds what InferenceState::logits() would.  logits_host may be NULL (leave them on device). */
 int xalm_cuda_forward(xalm_cuda_model* m, int token, int pos, int mode, float* logits_host);
+/* forward(OUTPUT_LOGITS) followed by Sampler::sample_argmax (sampler.cpp:3-16, FLT_MIN-seeded running maximum, first
+ * maximum wins) on the device: only the 4-byte token id crosses PCIe.  Leaves the host logits buffer untouched. */
+int xalm_cuda_forward_argmax(xalm_cuda_model* m, int token, int pos, int* next_token);
 /* Enqueue only (no host sync, logits stay on the device): the device-timed leg of bench.py. */
 int xalm_cuda_forward_async(xalm_cuda_model* m, int token, int pos, int mode);
 int xalm_cuda_sync(xalm_cuda_model* m);

@@ -177,3 +177,17 @@ def test_full_size_mistral_7b_q8_0_parity():
     assert gm.active_bytes(0) == active_bytes_formula(config, 34 / 32, 0) == om.active_bytes(0)
     assert abs(gm.active_bytes(0) / 1e9 - 7.555) < 0.01
     gm.close(); om.close()
+
+
+def test_device_sampler_matches_host_sampler():
+    """xalm_cuda_forward_argmax == Model.forward + Sampler.sample_argmax (incl. first-maximum-wins), greedy loop of 24 tokens."""
+    config, om, gm = synth_pair("tiny", "q8_0", seed=21, std=0.06)
+    state, sampler = InferenceState(config), Sampler(config)
+    tok_h = tok_d = 5
+    for pos in range(24):
+        gm.forward(state, tok_h, pos, 1)
+        nxt_h = sampler.sample_argmax(state)
+        nxt_d = gm.forward_argmax(tok_h, pos)      # same input token: the KV row is simply rewritten with the same values
+        assert nxt_d == nxt_h == oracle.sample_argmax(om.forward(tok_h, pos, 1))
+        tok_h = nxt_h
+    gm.close(); om.close()

@@ -271,6 +271,24 @@ __global__ void __launch_bounds__((TMA_NW + 1) * 32, 1) matvec_tma_kernel(const 
 	}
 
 	// ===================== consumers =====================
+	// the rmsnorm weights do not depend on the previous kernel: request this thread's share (up to 8 chunks = rows of 8192)
+	// before the dependency wait, so the scale pass below does not sit on an L2 round trip
+	constexpr int GPRE = 8;
+	float4 gpre[NORM ? GPRE : 1];
+	if (NORM) {
+#pragma unroll
+		for (int c = 0; c < GPRE; c++) {
+			const int i = (int) threadIdx.x * 4 + c * TMA_NW * 32 * 4;
+			if (i < a.n) {
+				if (a.norm_type == XALM_F32) gpre[c] = ld_act4(reinterpret_cast<const float*>(a.norm_w) + i);
+				else {
+					const uint2 gv = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(a.norm_w) + i);
+					gpre[c] = make_float4(__uint_as_float(gv.x << 16), __uint_as_float(gv.x & 0xFFFF0000u), __uint_as_float(gv.y << 16),
+					                      __uint_as_float(gv.y & 0xFFFF0000u));
+				}
+			}
+		}
+	}
 	pdl_wait(); // activations / KV ring of earlier kernels are visible from here on
 	tl_mark(tl, 2);
 	if (a.epi == EPI_QKV && blockIdx.x == 0 && a.step->kv_sink > 0) {
@@ -346,7 +364,17 @@ __global__ void __launch_bounds__((TMA_NW + 1) * 32, 1) matvec_tma_kernel(const 
 #pragma unroll
 			for (int i = 0; i < TMA_NW; i++) tot += s_red[i];
 			const float scale = 1.0f / sqrtf(tot / (float) a.n + a.norm_eps);
-			for (int i = threadIdx.x * 4; i < a.n; i += TMA_NW * 32 * 4) { // same elements this thread wrote above
+#pragma unroll
+			for (int c = 0; c < GPRE; c++) { // same elements this thread wrote above
+				const int i = (int) threadIdx.x * 4 + c * TMA_NW * 32 * 4;
+				if (i < a.n) {
+					float4 v = *reinterpret_cast<float4*>(xb + xpos(i));
+					const float4 g = gpre[c];
+					v.x = v.x * scale * g.x; v.y = v.y * scale * g.y; v.z = v.z * scale * g.z; v.w = v.w * scale * g.w; // infer.cpp:233-235
+					*reinterpret_cast<float4*>(xb + xpos(i)) = v;
+				}
+			}
+			for (int i = threadIdx.x * 4 + GPRE * TMA_NW * 32 * 4; i < a.n; i += TMA_NW * 32 * 4) { // rows longer than 8192
 				float4 v = *reinterpret_cast<float4*>(xb + xpos(i));
 				float4 g;
 				if (a.norm_type == XALM_F32) g = ld_act4(reinterpret_cast<const float*>(a.norm_w) + i);

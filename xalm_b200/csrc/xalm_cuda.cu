@@ -355,6 +355,40 @@ __global__ void dequant_kernel(int type, const uint8_t* __restrict__ src, size_t
 		dst[i] = decode_disk_elem(type, src, i);
 }
 
+// Sampler::sample_argmax (sampler.cpp:3-16) on the device: running maximum seeded with FLT_MIN (the reference's quirk: with no
+// logit above 1.18e-38 the answer is 0), strict '>' so the FIRST maximum wins.  One CTA.
+__global__ void argmax_kernel(const float* __restrict__ logits, int n, int* __restrict__ out) {
+	__shared__ float s_v[32];
+	__shared__ int s_i[32];
+	float best = 1.17549435e-38f; // numeric_limits<float>::min()
+	int bi = 0;
+	for (int i = threadIdx.x; i < n; i += blockDim.x) {
+		const float v = logits[i];
+		if (v > best) { best = v; bi = i; }
+	}
+	auto better = [](float v, int i, float bv, int b) { return v > bv || (v == bv && i < b); };
+	// a thread that saw nothing above the seed keeps index 0, which the tie rule turns into "lowest index": patch it to n so real hits win
+	if (best == 1.17549435e-38f && bi == 0 && !(logits[0] > 1.17549435e-38f)) bi = n;
+	for (int o = 16; o > 0; o >>= 1) {
+		const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+		const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+		if (better(ov, oi, best, bi)) { best = ov; bi = oi; }
+	}
+	if ((threadIdx.x & 31) == 0) { s_v[threadIdx.x >> 5] = best; s_i[threadIdx.x >> 5] = bi; }
+	__syncthreads();
+	if (threadIdx.x < 32) {
+		const int nw = (blockDim.x + 31) / 32;
+		best = threadIdx.x < nw ? s_v[threadIdx.x] : 1.17549435e-38f;
+		bi = threadIdx.x < nw ? s_i[threadIdx.x] : n;
+		for (int o = 16; o > 0; o >>= 1) {
+			const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+			const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+			if (better(ov, oi, best, bi)) { best = ov; bi = oi; }
+		}
+		if (threadIdx.x == 0) *out = bi >= n ? 0 : bi;
+	}
+}
+
 __global__ void residual_add_kernel(float* __restrict__ x, const float* __restrict__ y, int n) {
 	pdl_launch_dependents();
 	pdl_wait();
@@ -1438,6 +1472,20 @@ int xalm_cuda_forward(xalm_cuda_model* m, int token, int pos, int mode, float* l
 	} else {
 		XALM_CUDA_CHECK(cudaStreamSynchronize(m->stream));
 	}
+	return XALM_OK;
+}
+
+// Model::forward + Sampler::sample_argmax with the sampler on the device: 4 bytes come back instead of vocab * 4
+int xalm_cuda_forward_argmax(xalm_cuda_model* m, int token, int pos, int* next_token) {
+	if (!next_token) return set_error(XALM_ERR_INVALID, "next_token is NULL");
+	XALM_TRY(xalm_cuda_forward_async(m, token, pos, XALM_OUTPUT_LOGITS));
+	int* d_out = reinterpret_cast<int*>(m->d_progress) + 8; // 64-byte scratch word block owned by the handle
+	argmax_kernel<<<1, 1024, 0, m->stream>>>(m->logits_full, m->c.vocab_size, d_out);
+	XALM_CUDA_CHECK(cudaGetLastError());
+	int* h_out = reinterpret_cast<int*>(m->h_logits); // pinned; the logits themselves are not copied by this call
+	XALM_CUDA_CHECK(cudaMemcpyAsync(h_out, d_out, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+	XALM_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+	*next_token = *h_out;
 	return XALM_OK;
 }
 

@@ -143,6 +143,12 @@ class Model:
         capi.check(capi.lib().xalm_cuda_forward(self._h, token, pos, mode, lg.ctypes.data_as(C.c_void_p)
                                                 if mode == InferenceMode.OUTPUT_LOGITS else None))
 
+    def forward_argmax(self, token: int, pos: int) -> int:
+        """forward + Sampler.sample_argmax with the sampler on the device (4 bytes back instead of the logits)."""
+        out = C.c_int(0)
+        capi.check(capi.lib().xalm_cuda_forward_argmax(self._h, token, pos, C.byref(out)))
+        return out.value
+
     def forward_async(self, token: int, pos: int, mode: int = InferenceMode.OUTPUT_LOGITS) -> None:
         capi.check(capi.lib().xalm_cuda_forward_async(self._h, token, pos, mode))
 
