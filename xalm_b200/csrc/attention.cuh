@@ -58,20 +58,42 @@ __global__ void __launch_bounds__(NW * 32) attn_decode_kernel(const AttnArgs a) 
 	int tl = -1;
 	if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) tl = tl_begin(300);
 	if (threadIdx.x == 0) l2_prefetch_slice(a.pf_ptr, a.pf_bytes, (int) (blockIdx.y * gridDim.x + blockIdx.x), (int) (gridDim.x * gridDim.y));
-	pdl_wait();
-	tl_mark(tl, 2);
 
+	// Everything that does not depend on the QKV kernel still running is done BEFORE the dependency wait: the split bounds (the
+	// step parameters were written before the graph was launched) and the first batch of K/V rows — only the row being written
+	// this step (kv_pos) and the re-rotated sink rows are fetched again afterwards.
 	const int kvh = blockIdx.y, split = blockIdx.x;
 	const int kv_len = a.kv_len_fixed >= 0 ? a.kv_len_fixed : a.step->kv_len;
+	const int kv_pos = a.kv_len_fixed >= 0 ? -1 : a.step->kv_pos;
+	const int kv_sink = a.kv_len_fixed >= 0 ? 0 : a.step->kv_sink;
 	const int slen = attn_split_len(kv_len, a.n_splits, a.min_split);
 	const int n_active = (kv_len + slen - 1) / slen;
-	if (split >= n_active) return;
 	const int t0 = split * slen, t1 = min(kv_len, t0 + slen);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int sub = lane / LPR, li = lane % LPR; // which row of the request, which 8-dim slice
 	const int kv_stride = a.n_kv_heads * HD;
 	const float inv_sqrt = 1.0f / sqrtf((float) HD);
+	const __half* kbase = a.k_cache + (size_t) kvh * HD + li * 8;
+	const __half* vbase = a.v_cache + (size_t) kvh * HD + li * 8;
+
+	uint4 kn[TB], vn[TB]; // next batch, requested one iteration ahead
+	auto fetch = [&](int tb) {
+#pragma unroll
+		for (int j = 0; j < TB; j++) {
+			const int t = tb + j * RPW + sub;
+			const int tc = t < t1 ? t : t0;
+			kn[j] = ld_stream16(kbase + (size_t) tc * kv_stride);
+			vn[j] = ld_stream16(vbase + (size_t) tc * kv_stride);
+		}
+	};
+	const int tb_first = t0 + warp * RPW * TB;
+	const bool early = a.kv_len_fixed < 0 && split < n_active && tb_first < t1;
+	if (early) fetch(tb_first);
+
+	pdl_wait();
+	tl_mark(tl, 2);
+	if (split >= n_active) return;
 
 	// this lane's 8 dims of each of the G query heads
 	float qf[G][8];
@@ -89,22 +111,16 @@ __global__ void __launch_bounds__(NW * 32) attn_decode_kernel(const AttnArgs a) 
 #pragma unroll
 		for (int i = 0; i < 8; i++) acc[g][i] = 0.f;
 	}
-
-	const __half* kbase = a.k_cache + (size_t) kvh * HD + li * 8;
-	const __half* vbase = a.v_cache + (size_t) kvh * HD + li * 8;
-
-	uint4 kn[TB], vn[TB]; // next batch, requested one iteration ahead
-	auto fetch = [&](int tb) {
+	if (early) { // rows the QKV kernel wrote this step: take them again now that it has completed
 #pragma unroll
 		for (int j = 0; j < TB; j++) {
-			const int t = tb + j * RPW + sub;
-			const int tc = t < t1 ? t : t0;
-			kn[j] = ld_stream16(kbase + (size_t) tc * kv_stride);
-			vn[j] = ld_stream16(vbase + (size_t) tc * kv_stride);
+			const int t = tb_first + j * RPW + sub;
+			if (t < t1 && (t == kv_pos || t < kv_sink)) {
+				kn[j] = ld_stream16(kbase + (size_t) t * kv_stride);
+				vn[j] = ld_stream16(vbase + (size_t) t * kv_stride);
+			}
 		}
-	};
-	const int tb_first = t0 + warp * RPW * TB;
-	if (tb_first < t1) fetch(tb_first);
+	} else if (tb_first < t1) fetch(tb_first);
 	for (int tb = tb_first; tb < t1; tb += NW * RPW * TB) {
 		uint4 kq[TB], vq[TB];
 		bool ok[TB];
