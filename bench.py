@@ -178,8 +178,10 @@ def run_reference(args):
 
 
 def workload_config(args, cfg) -> dict:
-    return {"workload": f"{args.shape} ({'Mistral-7B-v0.2' if args.shape == 'm7' else args.shape} architecture) random-init {args.wtype}, "
-                        f"batch-1 decode, 4k context" if args.ctx == 4096 else f"{args.shape} {args.wtype} batch-1 decode ctx {args.ctx}",
+    depth = f" DEPTH-REDUCED to {args.layers} layers" if getattr(args, "layers", 0) else ""
+    return {"workload": (f"{args.shape} ({'Mistral-7B-v0.2' if args.shape == 'm7' else args.shape} architecture) random-init {args.wtype}, "
+                         f"batch-1 decode, 4k context" if args.ctx == 4096 else f"{args.shape} {args.wtype} batch-1 decode ctx {args.ctx}") + depth,
+            "n_layers": cfg["n_layers"],
             "shape": args.shape, "weight_format": args.wtype, "context": cfg["max_seq_len"], "batch": 1,
             "positions": "spread uniformly over [0, context)", "l2": "inputs larger than L2 (weights streamed from HBM every step)",
             "parallelism": f"tp{args.gpus}"}
@@ -374,6 +376,9 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-tokens", type=int, default=6, help="tokens the CPU baseline decodes (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers", type=int, default=0, help="depth-reduced variant of --shape (stated in config.workload); 0 = full depth")
+    ap.add_argument("--past-window", action="store_true",
+                    help="also time steps at positions >= ctx: the KV ring is full (kv_len = ctx), 2 attention sinks active (infer.cpp:608-613)")
     ap.add_argument("--no-prefill", action="store_true", help="skip the perplexity-mode summary appended to the decode line at N=1")
     ap.add_argument("--workload", default="decode", choices=["decode", "perplexity"],
                     help="decode = BASELINE config[1] (the headline metric); perplexity = config[2]: batched prefill of a 4k-token input")
@@ -413,7 +418,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    cfg_full = synth.model_config(args.shape)
+    cfg_full = synth.model_config(args.shape, **({"n_layers": args.layers} if args.layers else {}))
     cfg = X.parse_config(synth.metadata_strings(cfg_full), args.ctx)
     wtype = T.parse(args.wtype)
     comm_id = None
@@ -484,6 +489,27 @@ def main():
         ms, e2e_s = float(t[0]), float(t[1])
     tps = args.steps / (ms / 1e3)
     e2e_tps = args.steps / e2e_s
+    past = None
+    if args.past_window:
+        n = min(args.steps, 64)
+        for i in range(3):
+            model.forward_async(toks[i], ctx + i, 1)
+        model.sync()
+        barrier()
+        e0.record()
+        for i in range(n):
+            model.forward_async(toks[i], ctx + 3 + i, 1)
+        e1.record()
+        barrier()
+        pms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([pms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            pms = float(t[0])
+        pb = float(model.active_bytes(ctx + 3))
+        past = {"positions": f"{ctx + 3}..{ctx + 2 + n} (ring full: kv_len = {ctx}, 2 attention sinks re-rotated every step)", "steps": n,
+                "value": n / (pms / 1e3), "unit": "tok/s", "ms_per_step": pms / n, "bytes_per_step_this_rank": pb,
+                "achieved_gbs_this_rank": pb * n / (pms / 1e3) / 1e9}
 
     # ---- roofline: whole step, and the dominant kernel (fused norm + gate|up matvec) timed alone ----
     peak, peak_src = measured_peak_gbs()
@@ -518,6 +544,8 @@ def main():
                           "frac_of_8000": step_gbs / 8000.0, "formula": "Model::active_bytes(pos) (model.cpp:12-35), mean over the timed positions"},
         "notes": f"weights generated+uploaded in {gen_s:.0f}s; host cores {os.cpu_count()}",
     }
+    if past:
+        line["past_window"] = past
 
     # ---- BASELINE config[2] beside it (N = 1): the batched prefill / perplexity pass on the same resident model ----
     if world == 1 and not args.no_prefill and cfg["head_dim"] in (64, 128):

@@ -68,6 +68,7 @@ static std::map<std::string, int>& tuning() {
 	    {"tma_rc", 0},       // 0 = auto, else force rows per tile (4 or 8)
 	    {"tma_ns_max", 4},   // most ring stages
 	    {"tma_ctas_per_sm", 2},
+	    {"tma_grid_even", 0}, // percent: shrink the persistent grid down to this fraction of the full one if that makes tiles % grid == 0
 	    {"tp_fused", 1},     // tensor parallel: fuse the two per-layer exchanges into the matvec kernels (push over NVLink + receive in the next prologue)
 	    {"tail_prefetch_mb", 8}, // each decode kernel pulls this many MB of the NEXT kernel's first weights into L2 once its own loads are issued
 	    {"prefill_split", 3}, // batched prefill operand precision: 1 = fp16 x fp16 (fastest; logits drift ~4e-2 over 32 layers), 2 = hi+lo fp16
@@ -174,6 +175,12 @@ static cudaError_t launch_tma_inst(const TmaArgs& ta, int max_ctas_per_sm, size_
 	int per_sm = it->second < max_ctas_per_sm ? it->second : max_ctas_per_sm;
 	int grid = num_sms() * per_sm;
 	if (grid > ta.n_tiles) grid = ta.n_tiles;
+	// few tiles per CTA (1.7 - 13 on a 7B model): an uneven split leaves the CTAs with one tile more alone at the end. Take the
+	// largest grid within `tma_grid_even` percent of the full one that divides the tile count, when there is one.
+	if (const int pct = tune("tma_grid_even")) {
+		for (int g = grid; g * 100 >= grid * pct; g--)
+			if (ta.n_tiles % g == 0) { grid = g; break; }
+	}
 	return launch_smem(kern, dim3(grid), dim3((TMA_NW + 1) * 32), smem, s, pdl, ta);
 }
 
