@@ -51,7 +51,7 @@ def test_dequant_wide_types_and_sizes():
 
 
 # (rows, cols): small/few-row shapes take the K-split config, >= 6144 rows the many-row config
-SHAPES = [(64, 256), (32, 512), (6144, 256)]
+SHAPES = [(64, 256), (32, 512), (128, 1024), (6144, 256)]   # rows of <= 64 pieces also take the 16-row short-row tiles
 
 
 @pytest.mark.parametrize("t", T.MATMUL_TYPES, ids=lambda t: t.name)

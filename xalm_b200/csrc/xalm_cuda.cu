@@ -68,6 +68,7 @@ static std::map<std::string, int>& tuning() {
 	    {"tma_rc", 0},       // 0 = auto, else force rows per tile (4 or 8)
 	    {"tma_ns_max", 4},   // most ring stages
 	    {"tma_ctas_per_sm", 2},
+	    {"tma_short_rows", 1}, // rows of <= 64 pieces without a norm prologue: 16-row tiles with 1-2 K-slices (all lanes busy)
 	    {"tma_grid_even", 0}, // percent: shrink the persistent grid down to this fraction of the full one if that makes tiles % grid == 0
 	    {"tp_fused", 1},     // tensor parallel: fuse the two per-layer exchanges into the matvec kernels (push over NVLink + receive in the next prologue)
 	    {"tail_prefetch_mb", 8}, // each decode kernel pulls this many MB of the NEXT kernel's first weights into L2 once its own loads are issued
@@ -194,6 +195,10 @@ static cudaError_t launch_tma_typed(const TmaArgs& ta, int RC, int KW, bool norm
 	XALM_TMA_CASE(8, 4)
 	XALM_TMA_CASE(4, 8)
 #undef XALM_TMA_CASE
+	// short rows (the row-split Wo / W2 under tensor parallelism: n = q_dim / P): 16-row tiles, one or two K-slices, so every lane
+	// of a warp has a piece to work on
+	if (!norm && RC == 16 && KW == 2) return launch_tma_inst<TYPE, 16, 2, false>(ta, grid, smem, s, pdl);
+	if (!norm && RC == 16 && KW == 1) return launch_tma_inst<TYPE, 16, 1, false>(ta, grid, smem, s, pdl);
 	return cudaErrorInvalidValue;
 }
 
@@ -231,6 +236,10 @@ static int launch_matvec_tma(const MatvecArgs& a, cudaStream_t s, bool pdl) {
 	// CTAs fit per SM with 17 KB stages — measured faster than 2 x (8 K-slices) for these, slower for Wo/W2 (profiles/)
 	bool norm_cfg = false;
 	if (a.norm_w != nullptr && ppu >= 16 && tune("tma_norm_kw4") && nu * ppu / 4 >= 32) { RC = 8; KW = 4; norm_cfg = true; }
+	if (a.norm_w == nullptr && vrows % 16 == 0 && tune("tma_short_rows")) {
+		if (nu * ppu <= 32) { RC = 16; KW = 1; }
+		else if (nu * ppu <= 64) { RC = 16; KW = 2; }
+	}
 	const int force = tune("mv_cfg_rows");
 	if (force) norm_cfg = false;
 	if (force == 88) { RC = 8; KW = 8; }
