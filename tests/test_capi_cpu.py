@@ -67,5 +67,12 @@ def test_no_cpu_fallback_without_a_device():
     m = Model.from_tensors({**c, "act": 1}, [])
     with pytest.raises(RuntimeError):
         m.forward(InferenceState(c), 0, 0)                                 # not on a device: no CPU path
+    with pytest.raises(RuntimeError):
+        m.prefill([1, 2, 3])                                               # nor for the batched path
+    with pytest.raises(capi.XalmError) as e:
+        capi.gemm(np.ones((4, 32), np.float32), np.zeros((32, 32), np.float16).view(np.uint8), T.F16.id, 32, 32)
+    assert e.value.status == 3
+    with pytest.raises(capi.XalmError):
+        capi.bench_gemm(128, 256, 64)
     with pytest.raises(capi.XalmError):
         m.cuda()
