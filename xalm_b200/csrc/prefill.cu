@@ -8,7 +8,8 @@
 // Data flow per layer (T = tokens in this call, all buffers in HBM, sized for Tp = ceil(T/128)*128 rows):
 //   x fp32 (T,dim) --rmsnorm_rows--> xb  [A tiles fp16]
 //   xb . Wqkv^T    --gemm, QKV epilogue (clip, RoPE at pos0+row, fp16)--> q (T,q_dim) fp16; K/V cache rows pos0..pos0+T-1
-//   causal attention over the fp16 cache (flash-style, mma.sync tiles, fp32 online softmax) --> xb2 [A tiles]
+//   causal attention over the fp16 cache: tcgen05 QK^T / PV with S and O in TMEM for head_dim 128 (attn_tc_kernel), mma.sync
+//   tiles for head_dim 64 (attn_prefill_kernel); fp32 online softmax either way --> xb2 [A tiles]
 //   xb2 . Wo^T     --gemm, residual epilogue--> x += .
 //   x --rmsnorm_rows--> xb;  xb . (W1|W3)^T --gemm, GLU epilogue act(g)*u--> hb [A tiles]
 //   hb . W2^T      --gemm, residual epilogue--> x += .
@@ -21,9 +22,11 @@
 // per GEMM (dequant_tiles_kernel: every format the decode path takes), which costs 2 bytes written + read per weight
 // against 2*T flops per weight: ~10 % of the GEMM at T = 4096.
 //
-// Numerics: tensor-core operands are fp16 with fp32 accumulation.  split=2 keeps the activations to ~fp32 by feeding
-// hi = fp16(a) and lo = fp16(a - hi) as two MMAs against the same weight tile.  Tolerance in tests: logits within 1e-2
-// of the token-at-a-time path (north star: "within max-abs 1e-2 (fp16)").
+// Numerics: tensor-core operands are fp16 with fp32 accumulation.  split=1 rounds every operand to fp16 (fastest; ten rounding
+// stages per layer add up to ~4e-2 on the logits of a 32-layer model).  split=2 keeps the activations to ~fp32 by feeding
+// hi = fp16(a) and lo = fp16(a - hi) as two MMAs against the same weight tile.  split=3 (default) does the same for the weights
+// (hi.hi + lo.hi + hi.lo) and for q and the softmax probabilities in attention: logits within ~1e-3 of the token-at-a-time
+// fp32 path at 32 layers x 4096 tokens.  Tolerance in tests: 1e-2 (north star: "within max-abs 1e-2 (fp16)").
 #define XALM_SECONDARY_TU
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
