@@ -66,6 +66,7 @@ struct MatvecArgs {
 	int n_recv;                  // 0 = off
 	int recv_idx;
 	float* x_out;                // the first CTAs store x + sum(partials) here: the residual stream after the exchange
+	unsigned int* err_flag;      // set to 1 when a wait for a peer's words times out (the host turns it into XALM_ERR_COMM)
 	uint2* xl;                   // local (dim,) {value, tag} words: the reducing CTAs publish the summed stream here, every CTA polls it
 	// L2 prefetcher hand-shake (prefetch.cuh): block 0 publishes "kernel #prog_idx of this token has started"
 	unsigned int* progress;

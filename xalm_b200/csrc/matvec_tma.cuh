@@ -183,6 +183,7 @@ struct TmaArgs {
 };
 
 constexpr int TMA_NW = 8; // consumer warps
+constexpr unsigned int XALM_SPIN_LIMIT = 1u << 23; // polls of a tagged word (~1 us each) before a tensor-parallel wait gives up
 
 __host__ __device__ inline size_t tma_smem_bytes(int type, int n, int RC, int U, int NS) {
 	size_t s = 0;
@@ -316,9 +317,11 @@ __global__ void __launch_bounds__((TMA_NW + 1) * 32, 1) matvec_tma_kernel(const 
 				for (int p = 0; p < a.n_recv; p++) {
 					const uint2* src = a.recv + (size_t) p * a.n + i; // four {value, tag} words; poll until all carry this exchange's tag
 					uint4 w0, w1;
+					unsigned int spins = 0;
 					do {
 						asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w0.x), "=r"(w0.y), "=r"(w0.z), "=r"(w0.w) : "l"(src));
 						asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w1.x), "=r"(w1.y), "=r"(w1.z), "=r"(w1.w) : "l"(src + 2));
+						if (++spins > XALM_SPIN_LIMIT) { if (a.err_flag) *a.err_flag = 1u; break; } // a peer died: report, do not hang the GPU
 					} while (w0.y != seq || w0.w != seq || w1.y != seq || w1.w != seq);
 					sum.x += __uint_as_float(w0.x); sum.y += __uint_as_float(w0.z); sum.z += __uint_as_float(w1.x); sum.w += __uint_as_float(w1.z);
 				}
@@ -345,9 +348,11 @@ __global__ void __launch_bounds__((TMA_NW + 1) * 32, 1) matvec_tma_kernel(const 
 				const unsigned int seq = a.step->ar_base + (unsigned int) a.recv_idx + 1u;
 				const uint2* src = a.xl + i;
 				uint4 w0, w1;
+				unsigned int spins = 0;
 				do {
 					asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w0.x), "=r"(w0.y), "=r"(w0.z), "=r"(w0.w) : "l"(src));
 					asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w1.x), "=r"(w1.y), "=r"(w1.z), "=r"(w1.w) : "l"(src + 2));
+					if (++spins > XALM_SPIN_LIMIT) { if (a.err_flag) *a.err_flag = 1u; break; }
 				} while (w0.y != seq || w0.w != seq || w1.y != seq || w1.w != seq);
 				v = make_float4(__uint_as_float(w0.x), __uint_as_float(w0.z), __uint_as_float(w1.x), __uint_as_float(w1.z));
 			} else {

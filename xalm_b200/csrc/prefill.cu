@@ -998,37 +998,40 @@ __global__ void __launch_bounds__(256) retile_kv_kernel(const __half* __restrict
 }
 
 constexpr int ATT_THREADS = 192;
+constexpr int ATT_BKV = 64; // keys per block
 template <bool PRECISE>
 struct AttnTcCfg {
 	static constexpr int NP = PRECISE ? 2 : 1;                 // operand planes for Q and P
+	static constexpr int NKV = PRECISE ? 2 : 1;                // K / V slots (the plain-fp16 variant runs two CTAs per SM instead)
 	static constexpr int Q_BYTES = NP * 2 * A_TILE_BYTES;      // 128 rows x 128 hd
-	static constexpr int P_BYTES = NP * 2 * A_TILE_BYTES;      // 128 rows x 128 keys
-	static constexpr int KV_BYTES = 2 * A_TILE_BYTES;          // one K block or one V^T block
-	static constexpr size_t SMEM = Q_BYTES + P_BYTES + 2 * KV_BYTES + 1024 + 256;
+	static constexpr int P_TILE = A_TILE_BYTES;                // 128 rows x 64 keys, one plane
+	static constexpr int P_BYTES = 2 * NP * P_TILE;            // double-buffered
+	static constexpr int KV_SLOT = A_TILE_BYTES;               // 64 keys x 128 hd (K, two 8 KB halves) or 128 hd x 64 keys (V^T)
+	static constexpr size_t SMEM = Q_BYTES + P_BYTES + 2 * NKV * KV_SLOT + 1024 + 256;
 };
 
 template <bool PRECISE>
-__global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const AttnTcArgs a) {
+__global__ void __launch_bounds__(ATT_THREADS, PRECISE ? 1 : 2) attn_tc_kernel(const AttnTcArgs a) {
 	using Cfg = AttnTcCfg<PRECISE>;
-	constexpr int NP = Cfg::NP;
+	constexpr int NP = Cfg::NP, NKV = Cfg::NKV;
 	extern __shared__ uint8_t smem_raw[];
 	const uint32_t raw_s = s_u32(smem_raw);
 	uint8_t* smem = smem_raw + (((raw_s + 1023u) & ~1023u) - raw_s);
 	uint8_t* sQ = smem;
-	uint8_t* sP = sQ + Cfg::Q_BYTES;
-	uint8_t* sK = sP + Cfg::P_BYTES;
-	uint8_t* sV = sK + Cfg::KV_BYTES;
-	uint64_t* bars = reinterpret_cast<uint64_t*>(sV + Cfg::KV_BYTES);
+	uint8_t* sP = sQ + Cfg::Q_BYTES;            // [2][NP][128 x 64]
+	uint8_t* sK = sP + Cfg::P_BYTES;            // [NKV][2 hd halves][64 keys x 64]
+	uint8_t* sV = sK + NKV * Cfg::KV_SLOT;      // [NKV][128 hd x 64 keys]
+	uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NKV * Cfg::KV_SLOT);
 	uint64_t* q_full = bars;          // tx
-	uint64_t* k_full = bars + 1;      // tx
-	uint64_t* k_empty = bars + 2;     // commit
-	uint64_t* v_full = bars + 3;      // tx
-	uint64_t* v_empty = bars + 4;     // commit
-	uint64_t* s_full = bars + 5;      // [2] commit
-	uint64_t* s_empty = bars + 7;     // [2] 4 softmax warps
-	uint64_t* p_full = bars + 9;      // 4 softmax warps
-	uint64_t* o_full = bars + 10;     // commit
-	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+	uint64_t* k_full = bars + 1;      // [2] tx
+	uint64_t* k_empty = bars + 3;     // [2] commit
+	uint64_t* v_full = bars + 5;      // [2] tx
+	uint64_t* v_empty = bars + 7;     // [2] commit
+	uint64_t* s_full = bars + 9;      // [2] commit
+	uint64_t* s_empty = bars + 11;    // [2] 4 softmax warps
+	uint64_t* p_full = bars + 13;     // [2] 4 softmax warps
+	uint64_t* o_full = bars + 15;     // [2] commit (alternating by block parity, so a waiter is never two phases behind)
+	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int qb = a.n_qb - 1 - (int) blockIdx.x; // longest first
@@ -1036,20 +1039,22 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const AttnTcArg
 	const int kvh = h / (a.n_heads / a.n_kv_heads);
 	const int q0 = qb * 128;
 	const int q_last = min(q0 + 128, a.T) - 1;
-	const int n_kb = (a.pos0 + q_last) / 128 + 1; // 128-key blocks any row of this tile sees
+	const int n_kb = (a.pos0 + q_last) / ATT_BKV + 1; // 64-key blocks any row of this tile sees
 
 	if (threadIdx.x == 0) {
-		mb_init(q_full, 1); mb_init(k_full, 1); mb_init(k_empty, 1); mb_init(v_full, 1); mb_init(v_empty, 1);
-		mb_init(&s_full[0], 1); mb_init(&s_full[1], 1); mb_init(&s_empty[0], 4); mb_init(&s_empty[1], 4);
-		mb_init(p_full, 4); mb_init(o_full, 1);
+		mb_init(q_full, 1);
+		for (int i = 0; i < 2; i++) {
+			mb_init(&k_full[i], 1); mb_init(&k_empty[i], 1); mb_init(&v_full[i], 1); mb_init(&v_empty[i], 1);
+			mb_init(&s_full[i], 1); mb_init(&s_empty[i], 4); mb_init(&p_full[i], 4); mb_init(&o_full[i], 1);
+		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
-	if (warp == 1) tmem_alloc(tmem_slot, 512);
+	if (warp == 1) tmem_alloc(tmem_slot, 256);
 	tc_fence_before();
 	__syncthreads();
 	tc_fence_after();
 	const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-	const uint32_t TM_S0 = tmem_base, TM_O = tmem_base + 256; // S[b] at columns 128*b, O_blk at 256
+	const uint32_t TM_S0 = tmem_base, TM_O = tmem_base + 128; // S[b] at columns 64*b, O at 128
 
 	if (warp == 0) {
 		if (lane == 0) {
@@ -1058,23 +1063,29 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const AttnTcArg
 			bulk_load(sQ, a.qt_hi + qoff, 2 * A_TILE_BYTES, q_full);
 			if (PRECISE) bulk_load(sQ + 2 * A_TILE_BYTES, a.qt_lo + qoff, 2 * A_TILE_BYTES, q_full);
 			for (int j = 0; j < n_kb; j++) {
-				const size_t off = ((size_t) (kvh * a.n_kb_total + j) * 2) * A_TILE_BYTES;
-				mb_wait(k_empty, (j & 1) ^ 1);
-				mb_expect_tx(k_full, Cfg::KV_BYTES);
-				bulk_load(sK, a.kt + off, Cfg::KV_BYTES, k_full);
-				mb_wait(v_empty, (j & 1) ^ 1);
-				mb_expect_tx(v_full, Cfg::KV_BYTES);
-				bulk_load(sV, a.vt + off, Cfg::KV_BYTES, v_full);
+				const int slot = j % NKV, use = j / NKV; // use-th fill of this slot
+				// the retiled cache holds 128-key tiles; block j is rows [64 (j & 1), +64) of K tile (kvh, j / 2, hd half) — a contiguous
+				// 8 KB run of whole 8-row atoms — and V^T tile (kvh, j / 2, j & 1)
+				const uint8_t* ksrc = a.kt + ((size_t) (kvh * a.n_kb_total + (j >> 1)) * 2) * A_TILE_BYTES + (size_t) (j & 1) * (A_TILE_BYTES / 2);
+				const uint8_t* vsrc = a.vt + ((size_t) (kvh * a.n_kb_total + (j >> 1)) * 2 + (j & 1)) * A_TILE_BYTES;
+				mb_wait(&k_empty[slot], (use & 1) ^ 1);
+				mb_expect_tx(&k_full[slot], Cfg::KV_SLOT);
+				bulk_load(sK + slot * Cfg::KV_SLOT, ksrc, A_TILE_BYTES / 2, &k_full[slot]);
+				bulk_load(sK + slot * Cfg::KV_SLOT + A_TILE_BYTES / 2, ksrc + A_TILE_BYTES, A_TILE_BYTES / 2, &k_full[slot]);
+				mb_wait(&v_empty[slot], (use & 1) ^ 1);
+				mb_expect_tx(&v_full[slot], Cfg::KV_SLOT);
+				bulk_load(sV + slot * Cfg::KV_SLOT, vsrc, A_TILE_BYTES, &v_full[slot]);
 			}
 		}
 		__syncwarp();
 	} else if (warp == 1) {
 		if (lane == 0) {
-			constexpr uint32_t idesc = instr_desc_f16(128, 128);
+			constexpr uint32_t idesc_s = instr_desc_f16(128, ATT_BKV); // S = Q K^T: 128 rows x 64 keys
+			constexpr uint32_t idesc_o = instr_desc_f16(128, 128);     // O += P V: 128 rows x 128 hd
 			const uint32_t q_s = s_u32(sQ), p_s = s_u32(sP), k_s = s_u32(sK), v_s = s_u32(sV);
 			auto issue_qk = [&](int j) {
-				const int b = j & 1;
-				mb_wait(k_full, j & 1);
+				const int b = j & 1, slot = j % NKV, use = j / NKV;
+				mb_wait(&k_full[slot], use & 1);
 				mb_wait(&s_empty[b], ((j >> 1) & 1) ^ 1);
 				tc_fence_after();
 #pragma unroll
@@ -1083,28 +1094,27 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const AttnTcArg
 					for (int t = 0; t < 2; t++) // hd halves
 #pragma unroll
 						for (int k = 0; k < 4; k++)
-							umma_f16(TM_S0 + 128 * b, smem_desc(q_s + (p * 2 + t) * A_TILE_BYTES) + 2 * k, smem_desc(k_s + t * A_TILE_BYTES) + 2 * k, idesc,
-							         (uint32_t) ((p | t | k) != 0));
-				umma_commit(k_empty);
+							umma_f16(TM_S0 + ATT_BKV * b, smem_desc(q_s + (p * 2 + t) * A_TILE_BYTES) + 2 * k,
+							         smem_desc(k_s + slot * Cfg::KV_SLOT + t * (A_TILE_BYTES / 2)) + 2 * k, idesc_s, (uint32_t) ((p | t | k) != 0));
+				umma_commit(&k_empty[slot]);
 				umma_commit(&s_full[b]);
 			};
 			mb_wait(q_full, 0);
 			issue_qk(0);
 			for (int j = 0; j < n_kb; j++) {
-				if (j + 1 < n_kb) issue_qk(j + 1);
-				mb_wait(p_full, j & 1);
-				mb_wait(v_full, j & 1);
+				if (j + 1 < n_kb) issue_qk(j + 1); // the tensor pipe works on the next scores while the softmax warps turn these into P
+				const int b = j & 1, slot = j % NKV, use = j / NKV;
+				mb_wait(&p_full[b], (j >> 1) & 1);
+				mb_wait(&v_full[slot], use & 1);
 				tc_fence_after();
 #pragma unroll
 				for (int p = 0; p < NP; p++)
 #pragma unroll
-					for (int t = 0; t < 2; t++) // key halves
-#pragma unroll
-						for (int k = 0; k < 4; k++)
-							umma_f16(TM_O, smem_desc(p_s + (p * 2 + t) * A_TILE_BYTES) + 2 * k, smem_desc(v_s + t * A_TILE_BYTES) + 2 * k, idesc,
-							         (uint32_t) ((j | p | t | k) != 0)); // O accumulates in TMEM over all key blocks
-				umma_commit(v_empty);
-				umma_commit(o_full);
+					for (int k = 0; k < 4; k++)
+						umma_f16(TM_O, smem_desc(p_s + (b * NP + p) * Cfg::P_TILE) + 2 * k, smem_desc(v_s + slot * Cfg::KV_SLOT) + 2 * k, idesc_o,
+						         (uint32_t) ((j | p | k) != 0)); // O accumulates in TMEM over all key blocks
+				umma_commit(&v_empty[slot]);
+				umma_commit(&o_full[b]);
 			}
 		}
 		__syncwarp();
@@ -1125,28 +1135,31 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const AttnTcArg
 			const int b = j & 1;
 			mb_wait(&s_full[b], (j >> 1) & 1);
 			tc_fence_after();
-			const bool need_mask = j * 128 + 127 > a.pos0 + q0; // some key of this block is beyond the tile's first row
-			const int lim = a.pos0 + row - j * 128;              // keys with index (inside the block) > lim are masked
-			float sv[128];
+			const bool need_mask = j * ATT_BKV + ATT_BKV - 1 > a.pos0 + q0; // some key of this block is beyond the tile's first row
+			const int lim = a.pos0 + row - j * ATT_BKV;                      // keys with index (inside the block) > lim are masked
+			float sv[ATT_BKV];
 			__syncwarp();
 #pragma unroll
-			for (int c = 0; c < 4; c++) tmem_ld32_issue(TM_S0 + lane_addr + 128 * b + 32 * c, sv + 32 * c);
+			for (int c = 0; c < ATT_BKV / 32; c++) tmem_ld32_issue(TM_S0 + lane_addr + ATT_BKV * b + 32 * c, sv + 32 * c);
 			tmem_wait_ld();
 			float mx = -INFINITY;
 			if (need_mask) {
 #pragma unroll
-				for (int i = 0; i < 128; i++) {
+				for (int i = 0; i < ATT_BKV; i++) {
 					if (i > lim) sv[i] = -INFINITY;
 					mx = fmaxf(mx, sv[i]);
 				}
 			} else {
 #pragma unroll
-				for (int i = 0; i < 128; i++) mx = fmaxf(mx, sv[i]);
+				for (int i = 0; i < ATT_BKV; i++) mx = fmaxf(mx, sv[i]);
 			}
-			if (j > 0) mb_wait(o_full, (j - 1) & 1); // P V of the previous block has completed: the P tile is free, O is quiescent
+			// this P buffer was last read by the P V of block j-2: it must have completed (it has, long ago, in steady state)
+			if (j >= 2) mb_wait(&o_full[b], ((j >> 1) - 1) & 1);
 			const bool grow = mx > m_run + TAU_RAW;   // block 0: m_run = -inf -> true, but there is nothing to rescale yet
 			if (j == 0) m_run = mx;
 			else if (__any_sync(0xffffffffu, grow)) {
+				// rare: O must be quiescent, i.e. the P V of block j-1 (the last one issued) has completed
+				mb_wait(&o_full[(j - 1) & 1], ((j - 1) >> 1) & 1);
 				const float m_new = grow ? mx : m_run;
 				const float corr = ex2((m_run - m_new) * c1); // 1 for the rows that keep their maximum
 				tc_fence_after();
@@ -1164,9 +1177,10 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const AttnTcArg
 			}
 			const float nm = -m_run * c1;
 			// ---- probabilities -> fp16 operand tile (hi, lo), row sum ----
+			uint8_t* pt = sP + (size_t) (b * NP) * Cfg::P_TILE;
 			float rs = 0.f;
 #pragma unroll
-			for (int g8 = 0; g8 < 16; g8++) { // 8 keys = one 16-byte chunk
+			for (int g8 = 0; g8 < ATT_BKV / 8; g8++) { // 8 keys = one 16-byte chunk
 				__half2 hh[4], ll[4];
 #pragma unroll
 				for (int i = 0; i < 4; i++) {
@@ -1178,10 +1192,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const AttnTcArg
 						ll[i] = __floats2half2_rn(p0 - f.x, p1 - f.y);
 					}
 				}
-				const int key = 8 * g8; // inside the 128-key block
-				const size_t off = (size_t) (key >> 6) * A_TILE_BYTES + tile_inner_off(r, key & 63);
-				*reinterpret_cast<uint4*>(sP + off) = *reinterpret_cast<const uint4*>(hh);
-				if (PRECISE) *reinterpret_cast<uint4*>(sP + 2 * A_TILE_BYTES + off) = *reinterpret_cast<const uint4*>(ll);
+				const size_t off = tile_inner_off(r, 8 * g8);
+				*reinterpret_cast<uint4*>(pt + off) = *reinterpret_cast<const uint4*>(hh);
+				if (PRECISE) *reinterpret_cast<uint4*>(pt + Cfg::P_TILE + off) = *reinterpret_cast<const uint4*>(ll);
 			}
 			l_run += rs;
 			tc_fence_before();
@@ -1189,10 +1202,13 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const AttnTcArg
 			__syncwarp();
 			if (lane == 0) {
 				mb_arrive(&s_empty[b]);
-				mb_arrive(p_full);
+				mb_arrive(&p_full[b]);
 			}
 		}
-		mb_wait(o_full, (n_kb - 1) & 1);
+		{ // the last P V (and with it every earlier one: MMAs complete in order)
+			const int jl = n_kb - 1;
+			mb_wait(&o_full[jl & 1], (jl >> 1) & 1);
+		}
 		tc_fence_after();
 		const float inv = 1.0f / l_run;
 #pragma unroll
@@ -1214,7 +1230,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const AttnTcArg
 	__syncthreads();
 	if (warp == 1) {
 		tc_fence_after();
-		tmem_dealloc(tmem_base, 512);
+		tmem_dealloc(tmem_base, 256);
 	}
 }
 

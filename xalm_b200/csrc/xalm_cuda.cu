@@ -723,6 +723,7 @@ struct xalm_cuda_model {
 	bool peer_ready = false;
 	bool tp_fused = false;            // exchanges fused into the matvec kernels (push + receive in the next prologue)
 	float* x_alt = nullptr;           // second residual-stream buffer (the fused exchange ping-pongs x)
+	unsigned int* h_err = nullptr;    // pinned: a tensor-parallel wait that gave up sets it
 	uint2* xl = nullptr;              // [2][dim] {value, tag} words: the summed stream published inside a receiving kernel
 	xalm::PeerArgs peer = {};
 	std::vector<void*> peer_opened;
@@ -853,6 +854,7 @@ void xalm_cuda_destroy(xalm_cuda_model* m) {
 	if (m->staging.flag) cudaFree(m->staging.flag);
 	if (m->h_step) cudaFreeHost(m->h_step);
 	if (m->h_logits) cudaFreeHost(m->h_logits);
+	if (m->h_err) cudaFreeHost(m->h_err);
 	if (m->own_stream) cudaStreamDestroy(m->own_stream);
 	delete m;
 }
@@ -1202,6 +1204,7 @@ static int enqueue_token(xalm_cuda_model* m, int mode, cudaStream_t s, int* n_la
 		a.step = m->d_step; a.n_recv = m->tp_size; a.recv_idx = idx;
 		a.recv = m->peer.recv[m->tp_rank] + (size_t) slot * 8 * c.dim;
 		a.xl = m->xl + (size_t) slot * c.dim;
+		a.err_flag = m->h_err; // pinned host word, written over PCIe only when a wait gives up
 		a.x = X[cur]; a.x_out = X[cur ^ 1];
 		cur ^= 1;
 	};
@@ -1396,6 +1399,8 @@ int xalm_cuda_finalize(xalm_cuda_model* m) {
 	XALM_TRY(m->da.alloc((void**) &m->d_step, sizeof(StepParams)));
 	XALM_CUDA_CHECK(cudaMallocHost((void**) &m->h_step, 64 * sizeof(StepParams)));
 	XALM_CUDA_CHECK(cudaMallocHost((void**) &m->h_logits, (size_t) c.vocab_size * sizeof(float)));
+	XALM_CUDA_CHECK(cudaMallocHost((void**) &m->h_err, 64));
+	memset(m->h_err, 0, 64);
 	{ // L2 prefetcher: the token's weight matrices in execution order
 		std::vector<PrefetchItem> items;
 		unsigned long long cum = 0;
@@ -1473,10 +1478,17 @@ int xalm_cuda_forward_async(xalm_cuda_model* m, int token, int pos, int mode) {
 	return XALM_OK;
 }
 
+// a tensor-parallel wait that timed out inside a kernel (a peer died): report it instead of hanging
+static int check_tp_error(xalm_cuda_model* m) {
+	if (m->h_err && *reinterpret_cast<volatile unsigned int*>(m->h_err))
+		return set_error(XALM_ERR_COMM, "tensor-parallel exchange timed out waiting for a peer rank");
+	return XALM_OK;
+}
+
 int xalm_cuda_sync(xalm_cuda_model* m) {
 	if (!m) return set_error(XALM_ERR_INVALID, "model is NULL");
 	XALM_CUDA_CHECK(cudaStreamSynchronize(m->stream));
-	return XALM_OK;
+	return check_tp_error(m);
 }
 
 int xalm_cuda_forward(xalm_cuda_model* m, int token, int pos, int mode, float* logits_host) {
@@ -1488,7 +1500,7 @@ int xalm_cuda_forward(xalm_cuda_model* m, int token, int pos, int mode, float* l
 	} else {
 		XALM_CUDA_CHECK(cudaStreamSynchronize(m->stream));
 	}
-	return XALM_OK;
+	return check_tp_error(m);
 }
 
 // Model::forward + Sampler::sample_argmax with the sampler on the device: 4 bytes come back instead of vocab * 4
