@@ -237,6 +237,15 @@ def perplexity_summary(model, cfg, capi, n_tok: int) -> dict:
     return out
 
 
+def gemm_traffic(args, n_tok):
+    """dram bytes of the gate|up GEMM from the committed ncu capture (profiles/kernel_traffic.json), when it is this workload"""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "kernel_traffic.json")))
+        return d.get(f"{args.shape}_gemm_w13_T{n_tok}_bytes")
+    except Exception:
+        return None
+
+
 def run_perplexity_workload(args):
     """BASELINE config[2]: perplexity mode on a 4k-token synthetic input.  A step = one batched pass over `--tokens` positions
     (every position's logits + softmax-at-target), weights resident.  `value` device-timed; `e2e` through Model.prefill with
@@ -338,7 +347,7 @@ def run_perplexity_workload(args):
         "e2e": {"value": e2e_tps, "unit": "tok/s", "h2d_bytes_per_step": int(2 * n_tok * 4), "d2h_bytes_per_step": int(n_tok * 4),
                 "perplexity": ppl},
         "gpu_launches": launches, "clocks": clocks.summary(),
-        "roofline": {"bound": "tensor", "achieved": k_tf, "peak": burst, "unit": "TFLOP/s", "frac": k_tf / burst, "traffic": None,
+        "roofline": {"bound": "tensor", "achieved": k_tf, "peak": burst, "unit": "TFLOP/s", "frac": k_tf / burst, "traffic": gemm_traffic(args, n_tok),
                      "kernel": f"gemm_tc_kernel (tcgen05, 128x256x64 tiles) gate|up {n_tok}x{N13}x{K13}", "ms_per_launch": k_ms,
                      "mma_per_product": mmas, "issued_tflops": k_tf * mmas, "issued_frac": k_tf * mmas / burst, "peak_source": src,
                      "note": "achieved counts ALGORITHMIC flops 2*T*N*K; precision mode 3 issues 3 fp16 MMAs per product (hi.hi + lo.hi + hi.lo)"},
