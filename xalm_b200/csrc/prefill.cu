@@ -1002,7 +1002,9 @@ constexpr int ATT_BKV = 64; // keys per block
 template <bool PRECISE>
 struct AttnTcCfg {
 	static constexpr int NP = PRECISE ? 2 : 1;                 // operand planes for Q and P
-	static constexpr int NKV = PRECISE ? 2 : 1;                // K / V slots (the plain-fp16 variant runs two CTAs per SM instead)
+	static constexpr int NKV = PRECISE ? 3 : 4;                // K / V ring depth: a block's tiles take ~1.5 us to arrive from L2 and are consumed in
+	                                                           // ~0.3 us, so the loads must run several blocks ahead (ncu: with one slot the softmax
+	                                                           // warps sat on s_full — the MMA thread was waiting for K — 22 % of all samples)
 	static constexpr int Q_BYTES = NP * 2 * A_TILE_BYTES;      // 128 rows x 128 hd
 	static constexpr int P_TILE = A_TILE_BYTES;                // 128 rows x 64 keys, one plane
 	static constexpr int P_BYTES = 2 * NP * P_TILE;            // double-buffered
@@ -1011,7 +1013,7 @@ struct AttnTcCfg {
 };
 
 template <bool PRECISE>
-__global__ void __launch_bounds__(ATT_THREADS, PRECISE ? 1 : 2) attn_tc_kernel(const AttnTcArgs a) {
+__global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const AttnTcArgs a) {
 	using Cfg = AttnTcCfg<PRECISE>;
 	constexpr int NP = Cfg::NP, NKV = Cfg::NKV;
 	extern __shared__ uint8_t smem_raw[];
@@ -1023,15 +1025,16 @@ __global__ void __launch_bounds__(ATT_THREADS, PRECISE ? 1 : 2) attn_tc_kernel(c
 	uint8_t* sV = sK + NKV * Cfg::KV_SLOT;      // [NKV][128 hd x 64 keys]
 	uint64_t* bars = reinterpret_cast<uint64_t*>(sV + NKV * Cfg::KV_SLOT);
 	uint64_t* q_full = bars;          // tx
-	uint64_t* k_full = bars + 1;      // [2] tx
-	uint64_t* k_empty = bars + 3;     // [2] commit
-	uint64_t* v_full = bars + 5;      // [2] tx
-	uint64_t* v_empty = bars + 7;     // [2] commit
-	uint64_t* s_full = bars + 9;      // [2] commit
-	uint64_t* s_empty = bars + 11;    // [2] 4 softmax warps
-	uint64_t* p_full = bars + 13;     // [2] 4 softmax warps
-	uint64_t* o_full = bars + 15;     // [2] commit (alternating by block parity, so a waiter is never two phases behind)
-	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+	uint64_t* k_full = bars + 1;      // [4] tx
+	uint64_t* k_empty = bars + 5;     // [4] commit
+	uint64_t* v_full = bars + 9;      // [4] tx
+	uint64_t* v_empty = bars + 13;    // [4] commit
+	uint64_t* s_full = bars + 17;     // [4] commit
+	uint64_t* s_empty = bars + 21;    // [4] 4 softmax warps
+	uint64_t* p_full = bars + 25;     // [2] 4 softmax warps
+	uint64_t* o_full = bars + 27;     // [2] commit (alternating by block parity, so a waiter is never two phases behind)
+	uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
+	constexpr int LA = NKV - 1;       // the scores of LA blocks ahead are already in flight on the tensor pipe (S ring of 4 in TMEM)
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int qb = a.n_qb - 1 - (int) blockIdx.x; // longest first
@@ -1043,18 +1046,19 @@ __global__ void __launch_bounds__(ATT_THREADS, PRECISE ? 1 : 2) attn_tc_kernel(c
 
 	if (threadIdx.x == 0) {
 		mb_init(q_full, 1);
-		for (int i = 0; i < 2; i++) {
+		for (int i = 0; i < 4; i++) {
 			mb_init(&k_full[i], 1); mb_init(&k_empty[i], 1); mb_init(&v_full[i], 1); mb_init(&v_empty[i], 1);
-			mb_init(&s_full[i], 1); mb_init(&s_empty[i], 4); mb_init(&p_full[i], 4); mb_init(&o_full[i], 1);
+			mb_init(&s_full[i], 1); mb_init(&s_empty[i], 4);
 		}
+		for (int i = 0; i < 2; i++) { mb_init(&p_full[i], 4); mb_init(&o_full[i], 1); }
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
-	if (warp == 1) tmem_alloc(tmem_slot, 256);
+	if (warp == 1) tmem_alloc(tmem_slot, 512);
 	tc_fence_before();
 	__syncthreads();
 	tc_fence_after();
 	const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tmem_slot);
-	const uint32_t TM_S0 = tmem_base, TM_O = tmem_base + 128; // S[b] at columns 64*b, O at 128
+	const uint32_t TM_S0 = tmem_base, TM_O = tmem_base + 256; // S[j & 3] at columns 64 * (j & 3), O at 256
 
 	if (warp == 0) {
 		if (lane == 0) {
@@ -1084,9 +1088,9 @@ __global__ void __launch_bounds__(ATT_THREADS, PRECISE ? 1 : 2) attn_tc_kernel(c
 			constexpr uint32_t idesc_o = instr_desc_f16(128, 128);     // O += P V: 128 rows x 128 hd
 			const uint32_t q_s = s_u32(sQ), p_s = s_u32(sP), k_s = s_u32(sK), v_s = s_u32(sV);
 			auto issue_qk = [&](int j) {
-				const int b = j & 1, slot = j % NKV, use = j / NKV;
+				const int b = j & 3, slot = j % NKV, use = j / NKV;
 				mb_wait(&k_full[slot], use & 1);
-				mb_wait(&s_empty[b], ((j >> 1) & 1) ^ 1);
+				mb_wait(&s_empty[b], ((j >> 2) & 1) ^ 1);
 				tc_fence_after();
 #pragma unroll
 				for (int p = 0; p < NP; p++)
@@ -1100,9 +1104,9 @@ __global__ void __launch_bounds__(ATT_THREADS, PRECISE ? 1 : 2) attn_tc_kernel(c
 				umma_commit(&s_full[b]);
 			};
 			mb_wait(q_full, 0);
-			issue_qk(0);
+			for (int j = 0; j < LA && j < n_kb; j++) issue_qk(j);
 			for (int j = 0; j < n_kb; j++) {
-				if (j + 1 < n_kb) issue_qk(j + 1); // the tensor pipe works on the next scores while the softmax warps turn these into P
+				if (j + LA < n_kb) issue_qk(j + LA); // the tensor pipe works on later scores while the softmax warps turn these into P
 				const int b = j & 1, slot = j % NKV, use = j / NKV;
 				mb_wait(&p_full[b], (j >> 1) & 1);
 				mb_wait(&v_full[slot], use & 1);
@@ -1132,15 +1136,15 @@ __global__ void __launch_bounds__(ATT_THREADS, PRECISE ? 1 : 2) attn_tc_kernel(c
 		const float TAU_RAW = 8.0f * sqrtf(128.0f);
 		float m_run = -INFINITY, l_run = 0.f; // m_run: maximum of the raw scores
 		for (int j = 0; j < n_kb; j++) {
-			const int b = j & 1;
-			mb_wait(&s_full[b], (j >> 1) & 1);
+			const int b = j & 1, sb = j & 3;
+			mb_wait(&s_full[sb], (j >> 2) & 1);
 			tc_fence_after();
 			const bool need_mask = j * ATT_BKV + ATT_BKV - 1 > a.pos0 + q0; // some key of this block is beyond the tile's first row
 			const int lim = a.pos0 + row - j * ATT_BKV;                      // keys with index (inside the block) > lim are masked
 			float sv[ATT_BKV];
 			__syncwarp();
 #pragma unroll
-			for (int c = 0; c < ATT_BKV / 32; c++) tmem_ld32_issue(TM_S0 + lane_addr + ATT_BKV * b + 32 * c, sv + 32 * c);
+			for (int c = 0; c < ATT_BKV / 32; c++) tmem_ld32_issue(TM_S0 + lane_addr + ATT_BKV * sb + 32 * c, sv + 32 * c);
 			tmem_wait_ld();
 			float mx = -INFINITY;
 			if (need_mask) {
@@ -1201,7 +1205,7 @@ __global__ void __launch_bounds__(ATT_THREADS, PRECISE ? 1 : 2) attn_tc_kernel(c
 			asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy writes of P -> visible to the MMA (async proxy)
 			__syncwarp();
 			if (lane == 0) {
-				mb_arrive(&s_empty[b]);
+				mb_arrive(&s_empty[sb]);
 				mb_arrive(&p_full[b]);
 			}
 		}
@@ -1230,7 +1234,7 @@ __global__ void __launch_bounds__(ATT_THREADS, PRECISE ? 1 : 2) attn_tc_kernel(c
 	__syncthreads();
 	if (warp == 1) {
 		tc_fence_after();
-		tmem_dealloc(tmem_base, 256);
+		tmem_dealloc(tmem_base, 512);
 	}
 }
 
