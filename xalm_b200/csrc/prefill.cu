@@ -251,6 +251,18 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t b
 	             "r"(bytes), "r"(s_u32(bar))
 	             : "memory");
 }
+// one lane of a converged warp (elect.sync): lets the compiler keep the tcgen05 issue in a warp-uniform branch
+__device__ __forceinline__ bool elect_one() {
+	uint32_t pred;
+	asm volatile(
+	    "{\n"
+	    ".reg .pred p;\n"
+	    "elect.sync _|p, 0xffffffff;\n"
+	    "selp.u32 %0, 1, 0, p;\n"
+	    "}\n"
+	    : "=r"(pred));
+	return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // whole warp: allocate `cols` TMEM columns (power of two >= 32), base address -> *slot (shared memory)
@@ -1083,45 +1095,68 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const AttnTcArg
 		}
 		__syncwarp();
 	} else if (warp == 1) {
-		if (lane == 0) {
-			constexpr uint32_t idesc_s = instr_desc_f16(128, ATT_BKV); // S = Q K^T: 128 rows x 64 keys
-			constexpr uint32_t idesc_o = instr_desc_f16(128, 128);     // O += P V: 128 rows x 128 hd
-			const uint32_t q_s = s_u32(sQ), p_s = s_u32(sP), k_s = s_u32(sK), v_s = s_u32(sV);
-			auto issue_qk = [&](int j) {
-				const int b = j & 3, slot = j % NKV, use = j / NKV;
-				mb_wait(&k_full[slot], use & 1);
-				mb_wait(&s_empty[b], ((j >> 2) & 1) ^ 1);
-				tc_fence_after();
+		// The whole warp runs the control flow (barrier waits included) and ONE elected lane issues the MMAs and commits inside a
+		// warp-uniform branch.  With the loop under `if (lane == 0)` instead, ncu showed ~210 instructions per 64-key block on this
+		// single thread (ELECT / PLOP3 / R2UR around every UTCHMMA) — the MMA issuer, not the tensor pipe (28 % active) or the
+		// softmax warps, was setting the pace.
+		constexpr uint32_t idesc_s = instr_desc_f16(128, ATT_BKV); // S = Q K^T: 128 rows x 64 keys
+		constexpr uint32_t idesc_o = instr_desc_f16(128, 128);     // O += P V: 128 rows x 128 hd
+		const uint32_t q_s = s_u32(sQ), p_s = s_u32(sP), k_s = s_u32(sK), v_s = s_u32(sV);
+		uint64_t qd[NP * 2], kd[NKV * 2], pd[2 * NP], vd[NKV]; // operand descriptors of every slot, built once
+#pragma unroll
+		for (int i = 0; i < NP * 2; i++) qd[i] = smem_desc(q_s + i * A_TILE_BYTES);
+#pragma unroll
+		for (int i = 0; i < NKV * 2; i++) kd[i] = smem_desc(k_s + (i >> 1) * Cfg::KV_SLOT + (i & 1) * (A_TILE_BYTES / 2));
+#pragma unroll
+		for (int i = 0; i < 2 * NP; i++) pd[i] = smem_desc(p_s + i * Cfg::P_TILE);
+#pragma unroll
+		for (int i = 0; i < NKV; i++) vd[i] = smem_desc(v_s + i * Cfg::KV_SLOT);
+		auto issue_qk = [&](int j) {
+			const int b = j & 3, slot = j % NKV, use = j / NKV;
+			mb_wait(&k_full[slot], use & 1);
+			mb_wait(&s_empty[b], ((j >> 2) & 1) ^ 1);
+			tc_fence_after();
+			if (elect_one()) {
+				uint64_t kd0 = kd[0], kd1 = kd[1];
+#pragma unroll
+				for (int i = 1; i < NKV; i++)
+					if (slot == i) { kd0 = kd[2 * i]; kd1 = kd[2 * i + 1]; }
+				const uint32_t d = TM_S0 + ATT_BKV * b;
 #pragma unroll
 				for (int p = 0; p < NP; p++)
 #pragma unroll
 					for (int t = 0; t < 2; t++) // hd halves
 #pragma unroll
-						for (int k = 0; k < 4; k++)
-							umma_f16(TM_S0 + ATT_BKV * b, smem_desc(q_s + (p * 2 + t) * A_TILE_BYTES) + 2 * k,
-							         smem_desc(k_s + slot * Cfg::KV_SLOT + t * (A_TILE_BYTES / 2)) + 2 * k, idesc_s, (uint32_t) ((p | t | k) != 0));
+						for (int k = 0; k < 4; k++) umma_f16(d, qd[p * 2 + t] + 2 * k, (t ? kd1 : kd0) + 2 * k, idesc_s, (uint32_t) ((p | t | k) != 0));
 				umma_commit(&k_empty[slot]);
 				umma_commit(&s_full[b]);
-			};
-			mb_wait(q_full, 0);
-			for (int j = 0; j < LA && j < n_kb; j++) issue_qk(j);
-			for (int j = 0; j < n_kb; j++) {
-				if (j + LA < n_kb) issue_qk(j + LA); // the tensor pipe works on later scores while the softmax warps turn these into P
-				const int b = j & 1, slot = j % NKV, use = j / NKV;
-				mb_wait(&p_full[b], (j >> 1) & 1);
-				mb_wait(&v_full[slot], use & 1);
-				tc_fence_after();
+			}
+			__syncwarp();
+		};
+		mb_wait(q_full, 0);
+		for (int j = 0; j < LA && j < n_kb; j++) issue_qk(j);
+		for (int j = 0; j < n_kb; j++) {
+			if (j + LA < n_kb) issue_qk(j + LA); // the tensor pipe works on later scores while the softmax warps turn these into P
+			const int b = j & 1, slot = j % NKV, use = j / NKV;
+			mb_wait(&p_full[b], (j >> 1) & 1);
+			mb_wait(&v_full[slot], use & 1);
+			tc_fence_after();
+			if (elect_one()) {
+				uint64_t vdd = vd[0];
 #pragma unroll
-				for (int p = 0; p < NP; p++)
+				for (int i = 1; i < NKV; i++)
+					if (slot == i) vdd = vd[i];
 #pragma unroll
-					for (int k = 0; k < 4; k++)
-						umma_f16(TM_O, smem_desc(p_s + (b * NP + p) * Cfg::P_TILE) + 2 * k, smem_desc(v_s + slot * Cfg::KV_SLOT) + 2 * k, idesc_o,
-						         (uint32_t) ((j | p | k) != 0)); // O accumulates in TMEM over all key blocks
+				for (int p = 0; p < NP; p++) {
+					const uint64_t pdd = b ? pd[NP + p] : pd[p];
+#pragma unroll
+					for (int k = 0; k < 4; k++) umma_f16(TM_O, pdd + 2 * k, vdd + 2 * k, idesc_o, (uint32_t) ((j | p | k) != 0)); // O accumulates over all blocks
+				}
 				umma_commit(&v_empty[slot]);
 				umma_commit(&o_full[b]);
 			}
+			__syncwarp();
 		}
-		__syncwarp();
 	} else {
 		const int quad = warp & 3;
 		const int r = quad * 32 + lane; // query row inside the tile = TMEM lane
