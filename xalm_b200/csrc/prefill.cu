@@ -33,6 +33,7 @@
 #include <float.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <string>
@@ -975,6 +976,7 @@ struct AttnTcArgs {
 	const uint8_t* vt;   // V^T tiles
 	ATiles o;            // xb2
 	int T, pos0, n_heads, n_kv_heads, n_qb, n_kb_total;
+	int dbg; // timing knock-outs (XALM_ATTN_DBG, results are then meaningless): 1 = no QK MMAs, 2 = no PV MMAs, 4 = no softmax math / P stores
 };
 
 // cache rows -> K tiles and V^T tiles.  grid (64-key blocks, kv heads), 256 threads.
@@ -1127,7 +1129,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const AttnTcArg
 #pragma unroll
 					for (int t = 0; t < 2; t++) // hd halves
 #pragma unroll
-						for (int k = 0; k < 4; k++) umma_f16(d, qd[p * 2 + t] + 2 * k, (t ? kd1 : kd0) + 2 * k, idesc_s, (uint32_t) ((p | t | k) != 0));
+						for (int k = 0; k < 4; k++)
+							if (!(a.dbg & 1)) umma_f16(d, qd[p * 2 + t] + 2 * k, (t ? kd1 : kd0) + 2 * k, idesc_s, (uint32_t) ((p | t | k) != 0));
 				umma_commit(&k_empty[slot]);
 				umma_commit(&s_full[b]);
 			}
@@ -1150,7 +1153,8 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const AttnTcArg
 				for (int p = 0; p < NP; p++) {
 					const uint64_t pdd = b ? pd[NP + p] : pd[p];
 #pragma unroll
-					for (int k = 0; k < 4; k++) umma_f16(TM_O, pdd + 2 * k, vdd + 2 * k, idesc_o, (uint32_t) ((j | p | k) != 0)); // O accumulates over all blocks
+					for (int k = 0; k < 4; k++)
+						if (!(a.dbg & 2)) umma_f16(TM_O, pdd + 2 * k, vdd + 2 * k, idesc_o, (uint32_t) ((j | p | k) != 0)); // O accumulates over all blocks
 				}
 				umma_commit(&v_empty[slot]);
 				umma_commit(&o_full[b]);
@@ -1219,7 +1223,7 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const AttnTcArg
 			uint8_t* pt = sP + (size_t) (b * NP) * Cfg::P_TILE;
 			float rs = 0.f;
 #pragma unroll
-			for (int g8 = 0; g8 < ATT_BKV / 8; g8++) { // 8 keys = one 16-byte chunk
+			for (int g8 = 0; g8 < ((a.dbg & 4) ? 0 : ATT_BKV / 8); g8++) { // 8 keys = one 16-byte chunk
 				__half2 hh[4], ll[4];
 #pragma unroll
 				for (int i = 0; i < 4; i++) {
@@ -1558,7 +1562,8 @@ int prefill_run(const PrefillModel& pm, PrefillScratch** scratch, const int* tok
 		t_begin("attention");
 		if (attn_tc) {
 			retile_kv_kernel<<<dim3(2 * n_kb_total, c.n_kv_heads), 256, 0, s>>>(P.k_cache, P.v_cache, pm.kv_dim, pos0 + T, n_kb_total, sc.kt.p, sc.vt.p);
-			AttnTcArgs at = {sc.qt_hi.p, precise ? sc.qt_lo.p : nullptr, sc.kt.p, sc.vt.p, xb2, T, pos0, c.n_heads, c.n_kv_heads, n_qb, n_kb_total};
+			AttnTcArgs at = {sc.qt_hi.p, precise ? sc.qt_lo.p : nullptr, sc.kt.p, sc.vt.p, xb2, T, pos0, c.n_heads, c.n_kv_heads, n_qb, n_kb_total,
+			                 getenv("XALM_ATTN_DBG") ? atoi(getenv("XALM_ATTN_DBG")) : 0};
 			XALM_TRY(precise ? launch_attn_tc<true>(at, s) : launch_attn_tc<false>(at, s));
 			launches++;
 		} else {
