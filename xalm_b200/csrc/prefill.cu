@@ -394,6 +394,9 @@ struct GemmArgs {
 	uint8_t* qt_hi;     // when set: q goes into 128-row x 64-column operand tiles ((head, row block, hd half) order) for attn_tc_kernel
 	uint8_t* qt_lo;     // instead of row-major q_out / q_lo
 	int n_qb;           // row blocks of 128
+	uint8_t* kt;        // when set (pos0 == 0, head_dim 128): K and V^T operand tiles of attn_tc_kernel are written here as well,
+	uint8_t* vt;        // so no re-tiling pass over the cache is needed
+	int n_kb_total;     // 128-key blocks per kv head in kt / vt
 	__half* k_cache;
 	__half* v_cache;
 	const float2* rope_cs; // (T, head_dim/2): {cos, sin}(pos * freq) per row, from rope_table_kernel
@@ -574,6 +577,20 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tc_kernel(const GemmArgs
 					            : region == 1 ? g.k_cache + (size_t) pos * g.kv_dim + j0 : g.v_cache + (size_t) pos * g.kv_dim + j0;
 					reinterpret_cast<uint4*>(dst)[0] = reinterpret_cast<const uint4*>(h)[0];
 					reinterpret_cast<uint4*>(dst)[1] = reinterpret_cast<const uint4*>(h)[1];
+					if (region > 0 && g.kt) { // the same values as operand tiles (key = pos: this path is only taken with pos0 == 0)
+						const int kvh = j0 >> 7, hc = j0 & 127;
+						const size_t blk = (size_t) (kvh * g.n_kb_total + (pos >> 7)) * 2;
+						if (region == 1) { // K tile (kv head, 128-key block, hd half): row = key, 64 hd columns
+							uint8_t* t = g.kt + (blk + (hc >> 6)) * A_TILE_BYTES;
+							*reinterpret_cast<uint4*>(t + tile_inner_off(pos & 127, hc & 63)) = reinterpret_cast<const uint4*>(h)[0];
+							*reinterpret_cast<uint4*>(t + tile_inner_off(pos & 127, (hc & 63) + 8)) = reinterpret_cast<const uint4*>(h)[1];
+						} else {           // V^T tile (kv head, 128-key block, key half): row = hd, 64 key columns; a warp covers 32 consecutive keys
+							uint8_t* t = g.vt + (blk + ((pos & 127) >> 6)) * A_TILE_BYTES;
+							const __half* hv = reinterpret_cast<const __half*>(h);
+#pragma unroll
+							for (int i = 0; i < 16; i++) *reinterpret_cast<__half*>(t + tile_inner_off(hc + i, pos & 63)) = hv[i];
+						}
+					}
 					if (region == 0 && g.q_lo) {
 						__half2 l[8];
 #pragma unroll
@@ -1475,8 +1492,8 @@ int prefill_run(const PrefillModel& pm, PrefillScratch** scratch, const int* tok
 	if (attn_tc) {
 		XALM_TRY(sc.qt_hi.ensure((size_t) c.n_heads * n_qb * 2 * A_TILE_BYTES, true, s));
 		if (precise) XALM_TRY(sc.qt_lo.ensure((size_t) c.n_heads * n_qb * 2 * A_TILE_BYTES, true, s));
-		XALM_TRY(sc.kt.ensure((size_t) c.n_kv_heads * n_kb_total * 2 * A_TILE_BYTES, false, s));
-		XALM_TRY(sc.vt.ensure((size_t) c.n_kv_heads * n_kb_total * 2 * A_TILE_BYTES, false, s));
+		XALM_TRY(sc.kt.ensure((size_t) c.n_kv_heads * n_kb_total * 2 * A_TILE_BYTES, true, s)); // zeroed: tail keys of the last tile must stay finite
+		XALM_TRY(sc.vt.ensure((size_t) c.n_kv_heads * n_kb_total * 2 * A_TILE_BYTES, true, s));
 	} else {
 		XALM_TRY(sc.q.ensure((size_t) Tp * pm.q_dim * 2, true, s));
 		if (precise) XALM_TRY(sc.q_lo.ensure((size_t) Tp * pm.q_dim * 2, true, s));
@@ -1558,10 +1575,13 @@ int prefill_run(const PrefillModel& pm, PrefillScratch** scratch, const int* tok
 		g.q_out = q; g.q_lo = q_lo; g.k_cache = P.k_cache; g.v_cache = P.v_cache; g.rope_cs = rope_cs;
 		g.q_dim = pm.q_dim; g.kv_dim = pm.kv_dim; g.head_dim = c.head_dim; g.pos0 = pos0; g.qkv_clip = c.qkv_clip;
 		if (attn_tc) { g.qt_hi = sc.qt_hi.p; g.qt_lo = precise ? sc.qt_lo.p : nullptr; g.n_qb = n_qb; }
+		const bool tiles_from_epilogue = attn_tc && pos0 == 0 && getenv("XALM_ATTN_RETILE") == nullptr; // later chunks re-tile the whole cache prefix
+		if (tiles_from_epilogue) { g.kt = sc.kt.p; g.vt = sc.vt.p; g.n_kb_total = n_kb_total; }
 		XALM_TRY(run(g, P.wqkv));
 		t_begin("attention");
 		if (attn_tc) {
-			retile_kv_kernel<<<dim3(2 * n_kb_total, c.n_kv_heads), 256, 0, s>>>(P.k_cache, P.v_cache, pm.kv_dim, pos0 + T, n_kb_total, sc.kt.p, sc.vt.p);
+			if (!tiles_from_epilogue)
+				retile_kv_kernel<<<dim3(2 * n_kb_total, c.n_kv_heads), 256, 0, s>>>(P.k_cache, P.v_cache, pm.kv_dim, pos0 + T, n_kb_total, sc.kt.p, sc.vt.p);
 			AttnTcArgs at = {sc.qt_hi.p, precise ? sc.qt_lo.p : nullptr, sc.kt.p, sc.vt.p, xb2, T, pos0, c.n_heads, c.n_kv_heads, n_qb, n_kb_total,
 			                 getenv("XALM_ATTN_DBG") ? atoi(getenv("XALM_ATTN_DBG")) : 0};
 			XALM_TRY(precise ? launch_attn_tc<true>(at, s) : launch_attn_tc<false>(at, s));
