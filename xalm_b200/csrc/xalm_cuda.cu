@@ -456,6 +456,23 @@ __global__ void peer_allreduce_residual_kernel(const PeerArgs pa, float* __restr
 	}
 }
 
+// Fused exchange, HYDRATE tokens: the classifier that would receive the last exchange of the token is not run, but the exchange
+// must still be CONSUMED before this rank moves on — the two-slot scheme is only safe while every rank executes
+// push(i), recv(i), push(i+1), ... (tests/test_tp_exchange_protocol.py shows the overwrite / deadlock without this).  One CTA polls
+// the tags of all P partials of that exchange and discards the values.
+__global__ void tp_drain_kernel(const uint2* __restrict__ recv, int n_ranks, int dim, int idx, const StepParams* step, unsigned int* err_flag) {
+	pdl_launch_dependents();
+	pdl_wait();
+	const unsigned int seq = step->ar_base + (unsigned int) idx + 1u;
+	for (int i = threadIdx.x; i < n_ranks * dim; i += blockDim.x) {
+		unsigned int tag, val, spins = 0;
+		do {
+			asm volatile("ld.volatile.global.v2.u32 {%0,%1}, [%2];" : "=r"(val), "=r"(tag) : "l"(recv + i));
+			if (++spins > xalm::XALM_SPIN_LIMIT) { if (err_flag) *err_flag = 1u; break; }
+		} while (tag != seq);
+	}
+}
+
 // standalone rmsnorm / rope for the op-level entry points (the hot path fuses both into the matvec kernel)
 __global__ void rmsnorm_kernel(float* o, const float* x, const uint8_t* w, int wtype, int size, float eps) {
 	__shared__ float s_red[32];
@@ -1278,6 +1295,13 @@ static int enqueue_token(xalm_cuda_model* m, int mode, cudaStream_t s, int* n_la
 				nl += 2;
 			}
 		}
+	}
+	if (fused && mode != XALM_OUTPUT_LOGITS && c.n_layers > 0 && !m->mega) { // nobody else receives the token's last exchange: drain it
+		const int idx = 2 * c.n_layers - 1;
+		e = launch(tp_drain_kernel, dim3(1), dim3(1024), s, pdl, (const uint2*) (m->peer.recv[m->tp_rank] + (size_t) (idx & 1) * 8 * c.dim),
+		           m->tp_size, c.dim, idx, (const StepParams*) m->d_step, m->h_err);
+		if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "tp drain launch failed: %s", cudaGetErrorString(e));
+		nl++;
 	}
 	if (mode == XALM_OUTPUT_LOGITS) { // final norm + classifier (infer.cpp:625-637)
 		MatvecArgs a = {};
