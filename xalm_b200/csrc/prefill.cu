@@ -1071,8 +1071,11 @@ __global__ void __launch_bounds__(ATT_THREADS, 1) attn_tc_kernel(const AttnTcArg
 	constexpr int LA = NKV - 1;       // the scores of LA blocks ahead are already in flight on the tensor pipe (S ring of 4 in TMEM)
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int qb = a.n_qb - 1 - (int) blockIdx.x; // longest first
-	const int h = blockIdx.y;
+	// CTAs are dispatched in linear order (x fastest): make that order longest-first over the WHOLE launch — all heads' last
+	// query block, then all heads' second-to-last, ... — so the causal tail is made of the shortest tiles, not of one head's longest
+	const int lin = (int) (blockIdx.y * gridDim.x + blockIdx.x);
+	const int qb = a.n_qb - 1 - lin / a.n_heads;
+	const int h = lin % a.n_heads;
 	const int kvh = h / (a.n_heads / a.n_kv_heads);
 	const int q0 = qb * 128;
 	const int q_last = min(q0 + 128, a.T) - 1;
