@@ -172,6 +172,10 @@ int xalm_cuda_tune(const char* key, int value);
  * stop and fetch the records — 4 x u64 each: kernel id (100+epi = TMA matvec, 200+epi = LDG matvec, 300 = attention),
  * %globaltimer (ns) of block 0 at entry, after the dependency wait, at exit. */
 int xalm_cuda_timeline(int n_records, unsigned long long* out, int* n_out);
+/* Same idea for the one-kernel-per-token decode path (decode_mega.cu; tune "mega_timeline" = 1 before the first forward):
+ * out receives n_phases x 4 u64 of CTA 0 (arrival at the hand-off, hand-off done, activations staged, phase done) followed by
+ * n_phases x grid arrival stamps of every CTA.  With out == NULL only n_phases / grid are returned (0 = token kernel not in use). */
+int xalm_cuda_mega_timeline(xalm_cuda_model* m, unsigned long long* out, size_t cap_words, int* n_phases, int* grid);
 
 /* ---- kernel micro-benchmark hook (bench.py roofline leg; README.md:62-84 `-k matmul`) ------------------- */
 /* Times `iters` back-to-back launches of the matvec kernel on resident weights of `type_id` (random bytes), rotating

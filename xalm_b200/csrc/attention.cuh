@@ -303,6 +303,7 @@ __global__ void __launch_bounds__(NW * 32) attn_decode_kernel(const AttnArgs a) 
 	}
 }
 
+#ifndef XALM_SECONDARY_TU // non-template kernel: defined once, in xalm_cuda.cu's translation unit
 // ---- attention probabilities for the `att` scratch argument of mha (model.h:289-307): test hook only, one CTA per
 //      head, the three passes of infer.cpp:340-349 as written. ----
 __global__ void attn_probs_kernel(const float* q, const __half* k_cache, float* att, int head_dim, int n_kv_heads,
@@ -340,5 +341,7 @@ __global__ void attn_probs_kernel(const float* q, const __half* k_cache, float* 
 	for (int i = 0; i < (blockDim.x + 31) / 32; i++) sum += s_red[i];
 	for (int t = threadIdx.x; t < kv_len; t += blockDim.x) at[t] /= sum;
 }
+
+#endif // XALM_SECONDARY_TU
 
 } // namespace xalm

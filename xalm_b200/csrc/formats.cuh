@@ -36,6 +36,21 @@ __host__ __device__ inline bool type_info(int t, TypeInfo* ti) {
 	return false;
 }
 
+// bytes of one 256-element "unit" of the unit-interleaved device layout (matvec_tma.cuh, decode_mega.cu); 0 = not a unit format
+__host__ __device__ inline int unit_bytes(int t) {
+	switch (t) {
+		case XALM_F32: return 1024;
+		case XALM_F16: case XALM_BF16: return 512;
+		case XALM_F8_E4M3: case XALM_F8_E5M2: case XALM_Q8: return 256;
+		case XALM_Q8_0: return 272;
+		case XALM_Q4_0: return 144;
+		case XALM_Q4_1: return 160;
+		case XALM_Q5_0: return 176;
+		case XALM_Q5_1: return 192;
+	}
+	return 0; // not a TMA-path format
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Scalar decode from the on-disk layout.
 // ---------------------------------------------------------------------------------------------------------

@@ -24,20 +24,6 @@
 
 namespace xalm {
 
-__host__ __device__ inline int unit_bytes(int t) {
-	switch (t) {
-		case XALM_F32: return 1024;
-		case XALM_F16: case XALM_BF16: return 512;
-		case XALM_F8_E4M3: case XALM_F8_E5M2: case XALM_Q8: return 256;
-		case XALM_Q8_0: return 272;
-		case XALM_Q4_0: return 144;
-		case XALM_Q4_1: return 160;
-		case XALM_Q5_0: return 176;
-		case XALM_Q5_1: return 192;
-	}
-	return 0; // not a TMA-path format
-}
-
 // on-disk rows -> unit-interleaved rows.  One thread per (row, unit).
 __global__ void repack_units_kernel(int t, const uint8_t* __restrict__ raw, size_t raw_stride, int rows, int n, uint8_t* __restrict__ dst,
                                     size_t dst_stride) {
@@ -86,36 +72,6 @@ __global__ void repack_units_kernel(int t, const uint8_t* __restrict__ raw, size
 	}
 }
 
-// ---- mbarrier / bulk-copy primitives ------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-	asm volatile(
-	    "{\n"
-	    ".reg .pred p;\n"
-	    "WAIT_%=:\n"
-	    "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-	    "@p bra DONE_%=;\n"
-	    "bra WAIT_%=;\n"
-	    "DONE_%=:\n"
-	    "}\n" ::"r"(smem_u32(bar)),
-	    "r"(parity)
-	    : "memory");
-}
-// global -> shared bulk copy (TMA, 1-D); completion is credited to `bar` in bytes.  16-byte aligned, size % 16 == 0.
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
-	             "r"(bytes), "r"(smem_u32(bar))
-	             : "memory");
-}
 __device__ __forceinline__ void consumer_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 // ---- per-format access to one piece of a unit held in shared memory --------------------------------------------------

@@ -27,8 +27,7 @@
 #include "attention.cuh"
 #include "matvec.cuh"
 #include "matvec_tma.cuh"
-#include "megakernel.cuh"
-#include "prefetch.cuh"
+#include "decode_mega.h"
 #include "prefill.h"
 
 namespace xalm {
@@ -55,11 +54,11 @@ static std::map<std::string, int>& tuning() {
 	    {"attn_splits", 0},  // 0 = auto (~1 CTA per SM, at most 32 splits per kv head)
 	    {"attn_min_split", 128},
 	    {"mv_cfg_rows", 0},  // 0 = auto, 1 = force config A (R4 KS1 NW4), 2 = force config B (R2 KS4 NW8)
-	    {"l2_prefetch", 0},  // EXPERIMENTAL, measured slower (profiles/r1_experiments.md): side-branch warp prefetching upcoming weights into L2
-	    {"l2_window_mb", 48},
-	    {"mega", 0},         // EXPERIMENTAL (not faster yet): run all layers of a token in one persistent kernel (megakernel.cuh) when the model allows
-	    {"mega_smem_kb", 200},
-	    {"mega_rc_small", 4},
+	    {"mega", 1},         // one persistent kernel per token (decode_mega.cu) when the model allows: single GPU, integer weight formats
+	    {"mega_smem_kb", 226}, // shared memory per CTA the token kernel may take (ring = what the staged activations leave)
+	    {"mega_ns_max", 16},
+	    {"mega_coop", 1},    // cooperative launch of the token kernel
+	    {"mega_timeline", 0}, // record per-phase %globaltimer stamps (xalm_cuda_mega_timeline)
 	    {"tma", 1},          // stream weights with cp.async.bulk into a shared-memory ring (matvec_tma.cuh)
 	    {"tma_smem_kb", 100}, // shared-memory budget per CTA for the TMA kernel (two kernels co-reside under PDL)
 	    {"tma_rc_small", 8}, // rows per tile when the matrix has few rows (Wo, W2)
@@ -745,20 +744,19 @@ struct xalm_cuda_model {
 	xalm::PeerArgs peer = {};
 	std::vector<void*> peer_opened;
 	unsigned int token_serial = 0;
-	// L2 prefetcher (prefetch.cuh)
-	PrefetchItem* d_pf_items = nullptr;
-	int n_pf_items = 0;
-	unsigned int* d_progress = nullptr;
-	cudaStream_t side_stream = nullptr;
-	cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-	// megakernel (megakernel.cuh)
+	int* d_argmax = nullptr;          // device-side sampler result
+	int* h_argmax = nullptr;          // pinned
+	// one persistent kernel per token (decode_mega.cu)
 	bool mega = false;
-	MkPhase* d_phases = nullptr;
-	int n_phases = 0;
+	DmPhase* d_phases[2] = {nullptr, nullptr}; // per mode: HYDRATE stops before the classifier
+	int n_phases[2] = {0, 0};
 	unsigned int* d_gbar = nullptr;
-	MkArgs mk_args = {};
-	size_t mk_smem = 0;
-	int mk_type = 0;
+	DmArgs dm_args = {};
+	size_t dm_smem = 0;
+	int dm_type = 0;
+	int dm_grid = 0;
+	unsigned long long* d_mega_tl = nullptr;
+	size_t mega_tl_words = 0;
 	// batched prefill (prefill.cu)
 	PrefillScratch* prefill = nullptr;
 	int last_prefill_launches = 0;
@@ -861,9 +859,7 @@ void xalm_cuda_destroy(xalm_cuda_model* m) {
 	if (m->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m->comm);
 	for (int i = 0; i < 64; i++)
 		if (m->h_step_ev_used[i]) cudaEventDestroy(m->h_step_ev[i]);
-	if (m->side_stream) cudaStreamDestroy(m->side_stream);
-	if (m->ev_fork) cudaEventDestroy(m->ev_fork);
-	if (m->ev_join) cudaEventDestroy(m->ev_join);
+	if (m->h_argmax) cudaFreeHost(m->h_argmax);
 	for (void* p : m->peer_opened) cudaIpcCloseMemHandle(p);
 	if (m->xchg) cudaFree(m->xchg);
 	m->da.free_all();
@@ -1063,113 +1059,98 @@ int xalm_cuda_upload_tensor(xalm_cuda_model* m, const char* name, int type_id, c
 
 } // extern "C" (templates below)
 
-// ---- megakernel plumbing ---------------------------------------------------------------------------------------------
-template <int TYPE>
-static cudaError_t launch_mega_typed(const MkArgs& mk, int grid, size_t smem, cudaStream_t s, bool pdl) {
-	static size_t attr_smem = 0;
-	auto kern = layer_megakernel<TYPE>;
-	if (smem > attr_smem) {
-		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem);
-		if (e != cudaSuccess) return e;
-		attr_smem = smem;
-	}
-	return launch_smem(kern, dim3(grid), dim3(MK_THREADS2), smem, s, pdl, mk);
-}
-static cudaError_t launch_mega(int type, const MkArgs& mk, int grid, size_t smem, cudaStream_t s, bool pdl) {
-	switch (type) {
-		case XALM_F32: return launch_mega_typed<XALM_F32>(mk, grid, smem, s, pdl);
-		case XALM_F16: return launch_mega_typed<XALM_F16>(mk, grid, smem, s, pdl);
-		case XALM_BF16: return launch_mega_typed<XALM_BF16>(mk, grid, smem, s, pdl);
-		case XALM_F8_E4M3: return launch_mega_typed<XALM_F8_E4M3>(mk, grid, smem, s, pdl);
-		case XALM_F8_E5M2: return launch_mega_typed<XALM_F8_E5M2>(mk, grid, smem, s, pdl);
-		case XALM_Q8: return launch_mega_typed<XALM_Q8>(mk, grid, smem, s, pdl);
-		case XALM_Q8_0: return launch_mega_typed<XALM_Q8_0>(mk, grid, smem, s, pdl);
-		case XALM_Q4_0: return launch_mega_typed<XALM_Q4_0>(mk, grid, smem, s, pdl);
-		case XALM_Q4_1: return launch_mega_typed<XALM_Q4_1>(mk, grid, smem, s, pdl);
-		case XALM_Q5_0: return launch_mega_typed<XALM_Q5_0>(mk, grid, smem, s, pdl);
-		case XALM_Q5_1: return launch_mega_typed<XALM_Q5_1>(mk, grid, smem, s, pdl);
-	}
-	return cudaErrorInvalidValue;
-}
-static void mk_cfg_of(int type, int* KW, int* RCS, int* U) {
-	const int ppu = pieces_per_unit(type);
-	*KW = ppu == 8 ? 4 : 8;
-	*RCS = 8;
-	*U = (*KW * 32) / ppu > 0 ? (*KW * 32) / ppu : 1;
-}
-
+// ---- token kernel plumbing (decode_mega.cu) -------------------------------------------------------------------------------
 static void fill_layer_args(xalm_cuda_model* m, int l, MatvecArgs* qkv, AttnArgs* at, MatvecArgs* wo, MatvecArgs* w13, MatvecArgs* w2);
 
-// Decide whether the token's layers can run as one megakernel and, if so, build its phase list on the device.
+// Decide whether a token can run as one persistent kernel and, if so, build its phase lists on the device.
 static int setup_megakernel(xalm_cuda_model* m) {
 	m->mega = false;
-	if (!tune("mega") || !tune("tma") || m->tp_size > 1) return XALM_OK;
+	if (!tune("mega") || m->tp_size > 1) return XALM_OK;
 	const xalm_config& c = m->c;
+	if (c.n_layers < 1) return XALM_OK;
 	const int type = m->layers[0].wqkv.m.type;
-	if (!unit_bytes(type)) return XALM_OK;
+	if (!dm_supported_type(type)) return XALM_OK;
 	const int G = c.n_heads / c.n_kv_heads;
 	if ((c.head_dim != 64 && c.head_dim != 128) || (G != 1 && G != 2 && G != 4 && G != 8)) return XALM_OK;
-	int KW, RCS, U;
-	mk_cfg_of(type, &KW, &RCS, &U);
+	const int ub = unit_bytes(type);
+	TypeInfo ti;
+	type_info(type, &ti);
 	int max_n = 0;
-	for (auto& L : m->layers) {
-		const WMat* ws[4] = {&L.wqkv.m, &L.wo.m, &L.w13.m, &L.w2.m};
-		for (const WMat* w : ws) {
-			if (w->type != type || w->n % 256 || w->rows % RCS || (w->flags & WMAT_FP8_NONFINITE)) return XALM_OK;
-			TypeInfo ti;
-			type_info(type, &ti);
-			if (ti.block > 1 && !w->layout_units) return XALM_OK;
-			if (w->n > max_n) max_n = w->n;
-		}
-	}
-	const size_t scratch = mk_attn_scratch_floats(c.head_dim, G);
-	const size_t xb_floats = scratch > (size_t) max_n ? scratch : (size_t) max_n;
-	const int slot_bytes = RCS * U * unit_bytes(type);
-	const size_t budget = (size_t) tune("mega_smem_kb") * 1024;
-	const size_t fixed = ((xb_floats * sizeof(float) + 127) / 128) * 128 + MK_GROUPS * 2 * KW * RCS * sizeof(float) + 32 * sizeof(float) + 512;
-	if (fixed + 2 * MK_GROUPS * (size_t) slot_bytes > budget) return XALM_OK;
-	int NS = (int) ((budget - fixed) / slot_bytes / MK_GROUPS); // ring slots per consumer group
-	if (NS > 8) NS = 8;
-	std::vector<MkPhase> ph;
+	auto takes = [&](const WMat& w) {
+		if (w.type != type || w.n % 256 || w.rows % DM_RC) return false;
+		if (ti.block > 1 && !w.layout_units) return false;
+		if (ti.block == 1 && w.s0 != (size_t) w.n) return false;
+		if (w.n > max_n) max_n = w.n;
+		return true;
+	};
+	for (auto& L : m->layers)
+		if (!takes(L.wqkv.m) || !takes(L.wo.m) || !takes(L.w13.m) || !takes(L.w2.m)) return XALM_OK;
+	if (!takes(m->wcls.m)) return XALM_OK;
+	const int grid = num_sms();
+	size_t xq_cap = dm_xq_bytes(max_n);
+	const size_t scratch = dm_attn_scratch_bytes(c.head_dim, G);
+	if (scratch > xq_cap) xq_cap = scratch;
+	const size_t norm_need = dm_xq_bytes(c.dim) + (size_t) c.dim * sizeof(float) + 128; // norm-fused staging parks raw x behind the limbs
+	if (norm_need > xq_cap) xq_cap = norm_need;
+	xq_cap = (xq_cap + 127) / 128 * 128;
+	const int slot_bytes = DM_RC * DM_U * ub;
+	const size_t budget = std::min<size_t>((size_t) tune("mega_smem_kb") * 1024, 227 * 1024);
+	int NS = 0;
+	for (int ns = tune("mega_ns_max"); ns >= 2; ns--)
+		if (dm_fixed_smem(xq_cap, ns) + (size_t) ns * slot_bytes <= budget) { NS = ns; break; }
+	if (NS < 2) return XALM_OK;
+	std::vector<DmPhase> ph;
+	int off = 0;
+	auto mv = [&](const MatvecArgs& a) {
+		DmPhase p = {};
+		p.kind = DM_MATVEC;
+		p.a = a;
+		const int vrows = a.epi == EPI_GLU ? 2 * a.d : a.d;
+		p.n_tiles = vrows / DM_RC;
+		p.kranges = (a.n / 256 + DM_U - 1) / DM_U;
+		p.tile_off = off;
+		off = (off + p.n_tiles) % grid;
+		ph.push_back(p);
+	};
 	for (int l = 0; l < c.n_layers; l++) {
 		MatvecArgs qkv, wo, w13, w2;
 		AttnArgs at;
 		fill_layer_args(m, l, &qkv, &at, &wo, &w13, &w2);
-		auto mv = [&](const MatvecArgs& a) {
-			MkPhase p = {};
-			p.kind = MK_MATVEC;
-			p.a = a;
-			const int vrows = a.epi == EPI_GLU ? 2 * a.d : a.d;
-			// rows per tile: 8, or 4 when 8-row tiles would leave the consumer groups badly balanced (Wo, W2)
-			int rc = RCS;
-			const int groups = num_sms() * MK_GROUPS;
-			if (tune("mega_rc_small") == 4 && vrows / 8 < 4 * groups && KW == 8) rc = 4;
-			p.pad = rc;
-			p.n_tiles = vrows / rc;
-			p.kranges = (a.n / 256 + U - 1) / U;
-			ph.push_back(p);
-		};
 		mv(qkv);
-		MkPhase pa = {};
-		pa.kind = MK_ATTN; pa.at = at; pa.G = G; pa.HD = c.head_dim;
+		DmPhase pa = {};
+		pa.kind = DM_ATTN; pa.at = at; pa.G = G; pa.HD = c.head_dim;
+		pa.tile_off = off;
+		off = (off + at.n_kv_heads * (G == 8 ? 2 : 1) * at.n_splits) % grid;
 		ph.push_back(pa);
 		mv(wo);
 		mv(w13);
 		mv(w2);
 	}
-	XALM_TRY(m->da.alloc((void**) &m->d_phases, ph.size() * sizeof(MkPhase)));
-	XALM_CUDA_CHECK(cudaMemcpy(m->d_phases, ph.data(), ph.size() * sizeof(MkPhase), cudaMemcpyHostToDevice));
+	m->n_phases[XALM_HYDRATE_KV_CACHE] = (int) ph.size();
+	{ // final norm + classifier (infer.cpp:625-637)
+		MatvecArgs a = {};
+		a.w = m->wcls.m; a.x = m->x; a.n = c.dim; a.d = m->vocab_l; a.epi = EPI_STORE;
+		a.norm_w = m->rms_final; a.norm_type = m->rms_final_type; a.norm_eps = c.norm_eps; a.out = m->logits;
+		mv(a);
+	}
+	m->n_phases[XALM_OUTPUT_LOGITS] = (int) ph.size();
+	DmPhase* d = nullptr;
+	XALM_TRY(m->da.alloc((void**) &d, ph.size() * sizeof(DmPhase)));
+	XALM_CUDA_CHECK(cudaMemcpy(d, ph.data(), ph.size() * sizeof(DmPhase), cudaMemcpyHostToDevice));
+	m->d_phases[0] = m->d_phases[1] = d; // HYDRATE runs the same list minus its last phase
 	XALM_TRY(m->da.alloc((void**) &m->d_gbar, 64));
 	XALM_CUDA_CHECK(cudaMemset(m->d_gbar, 0, 64));
-	m->n_phases = (int) ph.size();
-	m->mk_args.phases = m->d_phases;
-	m->mk_args.n_phases = m->n_phases;
-	m->mk_args.NS = NS;
-	m->mk_args.slot_bytes = slot_bytes;
-	m->mk_args.xb_floats = (int) xb_floats;
-	m->mk_args.gbar = m->d_gbar;
-	m->mk_smem = fixed + (size_t) MK_GROUPS * NS * slot_bytes + 2 * MK_GROUPS * 8 * sizeof(uint64_t);
-	m->mk_type = type;
+	m->mega_tl_words = (size_t) ph.size() * (4 + grid);
+	XALM_TRY(m->da.alloc((void**) &m->d_mega_tl, m->mega_tl_words * sizeof(unsigned long long)));
+	XALM_CUDA_CHECK(cudaMemset(m->d_mega_tl, 0, m->mega_tl_words * sizeof(unsigned long long)));
+	m->dm_args.NS = NS;
+	m->dm_args.slot_bytes = slot_bytes;
+	m->dm_args.xq_cap = (int) xq_cap;
+	m->dm_args.gbar = m->d_gbar;
+	m->dm_args.err = m->h_err;
+	m->dm_smem = dm_fixed_smem(xq_cap, NS) + (size_t) NS * slot_bytes;
+	m->dm_type = type;
+	m->dm_grid = grid;
 	m->mega = true;
 	return XALM_OK;
 }
@@ -1183,28 +1164,23 @@ static int enqueue_token(xalm_cuda_model* m, int mode, cudaStream_t s, int* n_la
 	const bool tp = m->tp_size > 1;
 	int nl = 0;
 	cudaError_t e;
-	const bool prefetch = m->d_pf_items != nullptr && tune("l2_prefetch") && !m->mega;
-	if (prefetch) { // fork: one warp on a side branch pulls upcoming weights into L2 (prefetch.cuh)
-		XALM_CUDA_CHECK(cudaMemsetAsync(m->d_progress, 0, sizeof(unsigned int), s));
-		XALM_CUDA_CHECK(cudaEventRecord(m->ev_fork, s));
-		XALM_CUDA_CHECK(cudaStreamWaitEvent(m->side_stream, m->ev_fork, 0));
-		const int n_items = mode == XALM_OUTPUT_LOGITS ? m->n_pf_items : m->n_pf_items - 1;
-		l2_prefetch_kernel<<<1, 32, 0, m->side_stream>>>(m->d_pf_items, n_items, m->d_progress, (unsigned long long) tune("l2_window_mb") << 20,
-		                                                  50ull * 1000 * 1000);
-		XALM_CUDA_CHECK(cudaGetLastError());
-		XALM_CUDA_CHECK(cudaEventRecord(m->ev_join, m->side_stream));
-		nl++;
-	}
 	e = launch(embed_kernel, dim3(4), dim3(256), s, false, m->embed_type, (const uint8_t*) m->embed_raw, m->embed_row_bytes,
 	                       c.dim, (const StepParams*) m->d_step, m->x);
 	if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "embed launch failed: %s", cudaGetErrorString(e));
 	nl++;
 	const int G = c.n_heads / c.n_kv_heads;
-	if (m->mega) {
-		XALM_CUDA_CHECK(cudaMemsetAsync(m->d_gbar, 0, sizeof(unsigned int), s));
-		e = launch_mega(m->mk_type, m->mk_args, num_sms(), m->mk_smem, s, false);
-		if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "megakernel launch failed: %s", cudaGetErrorString(e));
+	if (m->mega) { // the whole token in one persistent kernel (decode_mega.cu)
+		XALM_CUDA_CHECK(cudaMemsetAsync(m->d_gbar, 0, 2 * sizeof(unsigned int), s)); // arrival counter + abort word
+		DmArgs da = m->dm_args;
+		da.phases = m->d_phases[mode];
+		da.n_phases = m->n_phases[mode];
+		da.tl = tune("mega_timeline") ? m->d_mega_tl : nullptr;
+		da.tl_phases = m->n_phases[XALM_OUTPUT_LOGITS];
+		e = dm_launch(m->dm_type, da, m->dm_grid, m->dm_smem, s, tune("mega_coop") != 0);
+		if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "token kernel launch failed: %s", cudaGetErrorString(e));
 		nl++;
+		if (n_launches) *n_launches = nl;
+		return XALM_OK;
 	}
 	// fused tensor-parallel exchange: Wo / W2 push their partial rows to every rank, the next norm-prologue kernel receives
 	const bool fused = tp && m->peer_ready && m->tp_fused;
@@ -1225,7 +1201,7 @@ static int enqueue_token(xalm_cuda_model* m, int mode, cudaStream_t s, int* n_la
 		a.x = X[cur]; a.x_out = X[cur ^ 1];
 		cur ^= 1;
 	};
-	for (int l = 0; l < c.n_layers && !m->mega; l++) {
+	for (int l = 0; l < c.n_layers; l++) {
 		LayerDev& L = m->layers[l];
 		MatvecArgs a_qkv, a_wo, a_w13, a_w2;
 		AttnArgs a_at;
@@ -1296,7 +1272,7 @@ static int enqueue_token(xalm_cuda_model* m, int mode, cudaStream_t s, int* n_la
 			}
 		}
 	}
-	if (fused && mode != XALM_OUTPUT_LOGITS && c.n_layers > 0 && !m->mega) { // nobody else receives the token's last exchange: drain it
+	if (fused && mode != XALM_OUTPUT_LOGITS && c.n_layers > 0) { // nobody else receives the token's last exchange: drain it
 		const int idx = 2 * c.n_layers - 1;
 		e = launch(tp_drain_kernel, dim3(1), dim3(1024), s, pdl, (const uint2*) (m->peer.recv[m->tp_rank] + (size_t) (idx & 1) * 8 * c.dim),
 		           m->tp_size, c.dim, idx, (const StepParams*) m->d_step, m->h_err);
@@ -1307,7 +1283,6 @@ static int enqueue_token(xalm_cuda_model* m, int mode, cudaStream_t s, int* n_la
 		MatvecArgs a = {};
 		a.w = m->wcls.m; a.x = m->x; a.n = c.dim; a.d = m->vocab_l; a.epi = EPI_STORE;
 		a.norm_w = m->rms_final; a.norm_type = m->rms_final_type; a.norm_eps = c.norm_eps; a.out = m->logits;
-		a.progress = m->d_progress; a.prog_idx = 4 * c.n_layers;
 		if (fused && c.n_layers > 0) set_recv(a, 2 * c.n_layers - 1);
 		XALM_TRY(launch_matvec(a, s, pdl && (!tp || fused)));
 		nl++;
@@ -1316,7 +1291,6 @@ static int enqueue_token(xalm_cuda_model* m, int mode, cudaStream_t s, int* n_la
 			nl++;
 		}
 	}
-	if (prefetch) XALM_CUDA_CHECK(cudaStreamWaitEvent(s, m->ev_join, 0)); // join the side branch
 	if (n_launches) *n_launches = nl;
 	return XALM_OK;
 }
@@ -1332,7 +1306,6 @@ static void fill_layer_args(xalm_cuda_model* m, int l, MatvecArgs* qkv, AttnArgs
 		a.norm_w = L.rms_att; a.norm_type = L.rms_att_type; a.norm_eps = c.norm_eps;
 		a.out = m->q; a.step = m->d_step; a.k_cache = L.k_cache; a.v_cache = L.v_cache; a.rope_freq = m->rope_freq;
 		a.q_dim = m->q_dim_l; a.kv_dim = m->kv_dim_l; a.head_dim = c.head_dim; a.qkv_clip = c.qkv_clip;
-		a.progress = m->d_progress; a.prog_idx = 4 * l;
 		*qkv = a;
 	}
 	{
@@ -1346,21 +1319,18 @@ static void fill_layer_args(xalm_cuda_model* m, int l, MatvecArgs* qkv, AttnArgs
 		MatvecArgs a = {};
 		a.w = L.wo.m; a.x = m->xb2; a.n = m->q_dim_l; a.d = c.dim;
 		a.epi = tp ? EPI_STORE : EPI_RESIDUAL; a.out = tp ? m->part : m->x;
-		a.progress = m->d_progress; a.prog_idx = 4 * l + 1;
 		*wo = a;
 	}
 	{ // ffn pre-norm + W1,W3 + act*gate
 		MatvecArgs a = {};
 		a.w = L.w13.m; a.x = m->x; a.n = c.dim; a.d = m->hidden_l; a.epi = EPI_GLU; a.glu_off = m->hidden_l; a.act = c.act;
 		a.norm_w = L.rms_ffn; a.norm_type = L.rms_ffn_type; a.norm_eps = c.norm_eps; a.out = m->hb;
-		a.progress = m->d_progress; a.prog_idx = 4 * l + 2;
 		*w13 = a;
 	}
 	{ // W2 + residual
 		MatvecArgs a = {};
 		a.w = L.w2.m; a.x = m->hb; a.n = m->hidden_l; a.d = c.dim;
 		a.epi = tp ? EPI_STORE : EPI_RESIDUAL; a.out = tp ? m->part : m->x;
-		a.progress = m->d_progress; a.prog_idx = 4 * l + 3;
 		*w2 = a;
 	}
 }
@@ -1418,33 +1388,16 @@ int xalm_cuda_finalize(xalm_cuda_model* m) {
 	m->attn_splits = attn_auto_splits(m->n_kv_heads_l);
 	XALM_TRY(fzero(&m->attn_acc, (size_t) m->n_kv_heads_l * m->attn_splits * G * c.head_dim));
 	XALM_TRY(fzero(&m->attn_ml, (size_t) m->n_kv_heads_l * m->attn_splits * G * 2));
-	XALM_TRY(m->da.alloc((void**) &m->tickets, m->n_kv_heads_l * sizeof(unsigned int)));
-	XALM_CUDA_CHECK(cudaMemset(m->tickets, 0, m->n_kv_heads_l * sizeof(unsigned int)));
+	XALM_TRY(m->da.alloc((void**) &m->tickets, 2 * m->n_kv_heads_l * sizeof(unsigned int))); // x2: the token kernel splits 8-head groups
+	XALM_CUDA_CHECK(cudaMemset(m->tickets, 0, 2 * m->n_kv_heads_l * sizeof(unsigned int)));
 	XALM_TRY(m->da.alloc((void**) &m->d_step, sizeof(StepParams)));
 	XALM_CUDA_CHECK(cudaMallocHost((void**) &m->h_step, 64 * sizeof(StepParams)));
 	XALM_CUDA_CHECK(cudaMallocHost((void**) &m->h_logits, (size_t) c.vocab_size * sizeof(float)));
 	XALM_CUDA_CHECK(cudaMallocHost((void**) &m->h_err, 64));
 	memset(m->h_err, 0, 64);
-	{ // L2 prefetcher: the token's weight matrices in execution order
-		std::vector<PrefetchItem> items;
-		unsigned long long cum = 0;
-		auto add = [&](const WMat& w) {
-			PrefetchItem it;
-			it.ptr = w.p0; it.bytes = (unsigned long long) w.s0 * w.rows; it.cum_start = cum;
-			cum += it.bytes;
-			items.push_back(it);
-		};
-		for (auto& L : m->layers) { add(L.wqkv.m); add(L.wo.m); add(L.w13.m); add(L.w2.m); }
-		add(m->wcls.m);
-		XALM_TRY(m->da.alloc((void**) &m->d_pf_items, items.size() * sizeof(PrefetchItem)));
-		XALM_CUDA_CHECK(cudaMemcpy(m->d_pf_items, items.data(), items.size() * sizeof(PrefetchItem), cudaMemcpyHostToDevice));
-		m->n_pf_items = (int) items.size();
-		XALM_TRY(m->da.alloc((void**) &m->d_progress, 64));
-		XALM_CUDA_CHECK(cudaMemset(m->d_progress, 0, 64));
-		XALM_CUDA_CHECK(cudaStreamCreateWithFlags(&m->side_stream, cudaStreamNonBlocking));
-		XALM_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
-		XALM_CUDA_CHECK(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
-	}
+	XALM_TRY(m->da.alloc((void**) &m->d_argmax, 64));
+	XALM_CUDA_CHECK(cudaMemset(m->d_argmax, 0, 64));
+	XALM_CUDA_CHECK(cudaMallocHost((void**) &m->h_argmax, 64));
 	XALM_TRY(setup_megakernel(m));
 	XALM_CUDA_CHECK(cudaDeviceSynchronize());
 	m->finalized = true;
@@ -1531,13 +1484,26 @@ int xalm_cuda_forward(xalm_cuda_model* m, int token, int pos, int mode, float* l
 int xalm_cuda_forward_argmax(xalm_cuda_model* m, int token, int pos, int* next_token) {
 	if (!next_token) return set_error(XALM_ERR_INVALID, "next_token is NULL");
 	XALM_TRY(xalm_cuda_forward_async(m, token, pos, XALM_OUTPUT_LOGITS));
-	int* d_out = reinterpret_cast<int*>(m->d_progress) + 8; // 64-byte scratch word block owned by the handle
-	argmax_kernel<<<1, 1024, 0, m->stream>>>(m->logits_full, m->c.vocab_size, d_out);
+	argmax_kernel<<<1, 1024, 0, m->stream>>>(m->logits_full, m->c.vocab_size, m->d_argmax);
 	XALM_CUDA_CHECK(cudaGetLastError());
-	int* h_out = reinterpret_cast<int*>(m->h_logits); // pinned; the logits themselves are not copied by this call
-	XALM_CUDA_CHECK(cudaMemcpyAsync(h_out, d_out, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+	// a pinned word of its own: the host logits buffer (InferenceState::_logits alias) stays untouched
+	XALM_CUDA_CHECK(cudaMemcpyAsync(m->h_argmax, m->d_argmax, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
 	XALM_CUDA_CHECK(cudaStreamSynchronize(m->stream));
-	*next_token = *h_out;
+	XALM_TRY(check_tp_error(m));
+	*next_token = *m->h_argmax;
+	return XALM_OK;
+}
+
+// Per-phase stamps of the token kernel (tune "mega_timeline" = 1 before the graph is captured): n_phases x 4 u64 of CTA 0
+// (arrival at the hand-off, hand-off done, activations staged, phase done), then n_phases x grid arrival stamps of every CTA.
+int xalm_cuda_mega_timeline(xalm_cuda_model* m, unsigned long long* out, size_t cap_words, int* n_phases, int* grid) {
+	if (!m || !n_phases || !grid) return set_error(XALM_ERR_INVALID, "NULL argument");
+	*n_phases = m->mega ? m->n_phases[XALM_OUTPUT_LOGITS] : 0;
+	*grid = m->mega ? m->dm_grid : 0;
+	if (!m->mega || !out) return XALM_OK;
+	XALM_CUDA_CHECK(cudaStreamSynchronize(m->stream));
+	const size_t words = std::min(cap_words, m->mega_tl_words);
+	XALM_CUDA_CHECK(cudaMemcpy(out, m->d_mega_tl, words * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
 	return XALM_OK;
 }
 
