@@ -9,13 +9,24 @@
 //
 //   * one PRODUCER warp per CTA walks the token's whole tile list and keeps a shared-memory ring (up to ~170 KB per SM,
 //     ~25 MB chip-wide) full with cp.async.bulk copies signalled through mbarriers.  Weights are immutable, so it never
-//     waits for a phase hand-off: while the consumers synchronise, stage activations or run attention, the ring fills with
-//     the NEXT phases' weights and HBM keeps streaming.  Small phases (Wo, QKV) are consumed straight from shared memory.
+//     waits for anybody: while the consumers wait for activations or run attention, the ring fills with the NEXT phases'
+//     weights and HBM keeps streaming.  Small phases (Wo, QKV) are consumed straight from shared memory.
 //   * eight CONSUMER warps per CTA run the integer-dot core (idp.cuh): activations are staged once per phase as block
 //     floating point (three int8 limbs per element), a 32-weight block costs 24 dp4a, ~1.3 issue slots per weight, so the
 //     consumers outrun the stream and catch up after every hand-off.
-//   * phases are separated by a grid-wide hand-off among the consumer warps: release-add on a counter in global memory,
-//     acquire-poll, then the activations written by other SMs are read with ld.global.cg (L2), never through L1.
+//   * there is NO grid barrier.  Every vector that crosses SMs (x, q, this token's K/V row, attention partials, xb2, hb) is
+//     "tagged": one 64-bit word per element, {value, tag of the producing phase}, written with one 8-byte store by the
+//     epilogue that computes it and polled by the consumer that stages it (ld.relaxed.gpu, L2) — the hand-off IS the data:
+//     no fence, no flag, no counter, one trip through L2 (measured: a trip costs ~1 us under a saturated weight stream, and
+//     a fence + counter + reload hand-off cost three of them, 5 times per layer).  A phase may overwrite a tagged vector in
+//     place because every reader of the old value has tiles the writer's own input depends on; a CTA without work in a
+//     phase does not read at all, and a reader accepts a NEWER tag, so nobody can wait for a tag that has been overwritten.
+//   * everything else a consumer needs after its input arrives is already on the SM: phase descriptors are fetched one
+//     phase ahead into shared memory, the token's scalars and the RoPE table are loaded once, norm weights are requested
+//     before the input is polled (all of these are read once per token, i.e. from DRAM behind the weight stream).
+//   * attention: split-K flash-decode as in attention.cuh, one (kv head, split) item per CTA, first K/V batch requested
+//     before q is polled; per-split partials are tagged, and the merge is DISTRIBUTED — CTA c merges outputs [32c, 32c+32)
+//     of all splits — instead of a fence + ticket + last-CTA chain.
 //   * tile t of a phase runs on CTA (t + tile_off) % grid with tile_off advanced by each phase's remainder, so the odd tile
 //     moves around and every SM streams the same number of bytes per token.
 //
@@ -33,10 +44,9 @@
 
 namespace xalm {
 
-constexpr unsigned int DM_SPIN_LIMIT = 1u << 21; // acquire-polls (~0.5 us each) before a hand-off wait gives up
+constexpr unsigned int DM_SPIN_LIMIT = 1u << 21; // polls (~0.5-1 us each) before a wait for another SM's data gives up
 
 __device__ __forceinline__ void dm_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-__device__ __forceinline__ float4 dm_ld_cg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
 
 // Every wait in this kernel is bounded: a wait that gives up raises the CTA's abort flag (later waits return at once), the
 // device-wide abort word gbar[1] (other CTAs stop waiting for this one) and the pinned host word the next synchronising call
@@ -62,61 +72,121 @@ __device__ __forceinline__ bool dm_mbar_wait(uint64_t* bar, uint32_t parity, vol
 	}
 }
 
-// grid-wide hand-off among the consumer warps of all CTAs: everything this CTA wrote is released, everything the others
-// wrote before their arrival is acquired.  `target` = arrivals expected so far (the counter only grows inside a launch).
-__device__ __forceinline__ void dm_handoff(unsigned int* ctr, unsigned int target, unsigned int* err, volatile int* s_abort) {
-	dm_bar(); // all consumer warps of this CTA have issued their stores
-	if (threadIdx.x == 0) {
-		__threadfence();
-		asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
-		unsigned int v, spins = 0;
-		for (;;) {
-			asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-			if (v >= target) break;
-			if ((++spins & 255u) == 0) {
-				unsigned int ab;
-				asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(ab) : "l"(ctr + 1) : "memory");
-				if (ab || *s_abort || spins > DM_SPIN_LIMIT) { // a CTA is missing: report, do not hang the GPU
-					*s_abort = 1;
-					asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(ctr + 1), "r"(1u) : "memory");
-					if (err) *err = 2u;
-					break;
-				}
-			}
-		}
+// ---- tagged words ----------------------------------------------------------------------------------------------------------
+struct DmAbort {
+	volatile int* s_abort;  // this CTA
+	unsigned int* g_abort;  // device-wide
+	unsigned int* err;      // pinned host word
+};
+__device__ __forceinline__ dm_tagged dm_pack(uint32_t bits, uint32_t tag) { return (dm_tagged) bits | ((dm_tagged) tag << 32); }
+__device__ __forceinline__ dm_tagged dm_packf(float v, uint32_t tag) { return dm_pack(__float_as_uint(v), tag); }
+__device__ __forceinline__ bool dm_fresh(dm_tagged w, uint32_t tag) { return (int) ((uint32_t) (w >> 32) - tag) >= 0; }
+__device__ __forceinline__ void dm_st(dm_tagged* p, dm_tagged w) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(w) : "memory"); }
+__device__ __forceinline__ void dm_st2(dm_tagged* p, dm_tagged w0, dm_tagged w1) {
+	asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ dm_tagged dm_ld(const dm_tagged* p) {
+	dm_tagged w;
+	asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+	return w;
+}
+__device__ __forceinline__ void dm_ld2(const dm_tagged* p, dm_tagged& a, dm_tagged& b) {
+	asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+// called every so often from a polling loop: has somebody given up, or is it time to?
+__device__ __forceinline__ bool dm_check_abort(const DmAbort& ab, unsigned int spins) {
+	unsigned int g;
+	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(ab.g_abort) : "memory");
+	if (g || *ab.s_abort || spins > DM_SPIN_LIMIT) {
+		*ab.s_abort = 1;
+		asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(ab.g_abort), "r"(1u) : "memory");
+		if (ab.err) *ab.err = 2u;
+		return true;
 	}
-	dm_bar();
+	return false;
+}
+// four consecutive tagged words (32-byte aligned) -> their values, once all four carry `tag` (or a newer one)
+struct DmQuad {
+	dm_tagged w[4];
+};
+__device__ __forceinline__ void dm_quad_issue(const dm_tagged* p, DmQuad& q) {
+	dm_ld2(p, q.w[0], q.w[1]);
+	dm_ld2(p + 2, q.w[2], q.w[3]);
+}
+__device__ __forceinline__ void dm_quad_wait(const dm_tagged* p, uint32_t tag, DmQuad& q, const DmAbort& ab) {
+	unsigned int spins = 0;
+	while (!(dm_fresh(q.w[0], tag) && dm_fresh(q.w[1], tag) && dm_fresh(q.w[2], tag) && dm_fresh(q.w[3], tag))) {
+		if ((++spins & 63u) == 0 && dm_check_abort(ab, spins)) break;
+		dm_quad_issue(p, q);
+	}
+}
+__device__ __forceinline__ float4 dm_quad_f4(const DmQuad& q) {
+	return make_float4(__uint_as_float((uint32_t) q.w[0]), __uint_as_float((uint32_t) q.w[1]), __uint_as_float((uint32_t) q.w[2]),
+	                   __uint_as_float((uint32_t) q.w[3]));
+}
+__device__ __forceinline__ dm_tagged dm_poll1(const dm_tagged* p, uint32_t tag, const DmAbort& ab) {
+	dm_tagged w = dm_ld(p);
+	unsigned int spins = 0;
+	while (!dm_fresh(w, tag)) {
+		if ((++spins & 63u) == 0 && dm_check_abort(ab, spins)) break;
+		w = dm_ld(p);
+	}
+	return w;
 }
 
-// ---- activation staging: x (global, written by other SMs) [-> rmsnorm] -> block floating point in shared memory ----------
-// norm weight chunk i..i+3 as fp32 (F32, or BF16 = bits << 16, types.h:322-325)
-__device__ __forceinline__ float4 dm_norm_w4(const MatvecArgs& a, int i) {
-	if (a.norm_type == XALM_F32) return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(a.norm_w) + i);
-	const uint2 packed = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(a.norm_w) + i);
-	return make_float4(__uint_as_float(packed.x << 16), __uint_as_float(packed.x & 0xFFFF0000u), __uint_as_float(packed.y << 16),
-	                   __uint_as_float(packed.y & 0xFFFF0000u));
+// ---- activation staging: tagged x (global, written by other SMs) [-> rmsnorm] -> block floating point in shared memory -----
+// norm weights of this thread's chunks (elements tid*4 + c*1024 ..+3), requested BEFORE the input is polled: they are
+// constants, but read once per token they come from DRAM, which behind a saturated weight stream is microseconds away.
+constexpr int DM_GC = 8; // chunks per thread covered by the early fetch (n <= 8192); longer rows fetch the rest late
+struct DmNormW {
+	uint2 g[DM_GC]; // BF16 weights, packed (the usual case: convert.py keeps 1-D tensors bf16); F32 weights are fetched late
+};
+__device__ __forceinline__ uint4 dm_norm_unpack(uint2 packed) { // BF16 = bits << 16, types.h:322-325
+	return make_uint4(packed.x << 16, packed.x & 0xFFFF0000u, packed.y << 16, packed.y & 0xFFFF0000u);
 }
-// rmsnorm-fused staging (infer.cpp:224-236): pass 1 pulls x from L2 (all loads of a thread in flight together), accumulates the
+__device__ __forceinline__ uint4 dm_norm_w4(const MatvecArgs& a, int i) {
+	if (a.norm_type == XALM_F32) return *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(a.norm_w) + i);
+	return dm_norm_unpack(*reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(a.norm_w) + i));
+}
+__device__ __forceinline__ void dm_norm_fetch(const MatvecArgs& a, DmNormW& w) {
+	if (a.norm_type == XALM_F32) { // pull the lines towards L2; the values are read after the reduction
+#pragma unroll
+		for (int c = 0; c < DM_GC; c++) {
+			const int i = (int) threadIdx.x * 4 + c * (DM_CW * 32 * 4);
+			if (i < a.n) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const float*>(a.norm_w) + i));
+		}
+		return;
+	}
+#pragma unroll
+	for (int c = 0; c < DM_GC; c++) {
+		const int i = (int) threadIdx.x * 4 + c * (DM_CW * 32 * 4);
+		if (i < a.n) w.g[c] = *reinterpret_cast<const uint2*>(reinterpret_cast<const uint16_t*>(a.norm_w) + i);
+	}
+}
+// rmsnorm-fused staging (infer.cpp:224-236): pass 1 polls x (all of a thread's chunks in flight together), accumulates the
 // sum of squares and parks the raw values in `stash` (the tail of the activation area, free while n = dim is being staged);
 // pass 2 scales, multiplies by the norm weight and quantises.
-__device__ __forceinline__ void dm_stage_norm(const MatvecArgs& a, const XqView& v, float* s_red, float* stash) {
+__device__ __forceinline__ void dm_stage_norm(const MatvecArgs& a, const dm_tagged* in_t, uint32_t tag, const XqView& v, float* s_red,
+                                              float* stash, const DmNormW& w, const DmAbort& ab) {
 	const int n = a.n;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 	constexpr int B = 4;
 	float ss = 0.f;
 	for (int i0 = tid * 4; i0 < n; i0 += B * DM_CW * 32 * 4) {
-		float4 xv[B];
+		DmQuad q[B];
 #pragma unroll
 		for (int c = 0; c < B; c++) {
 			const int i = i0 + c * (DM_CW * 32 * 4);
-			if (i < n) xv[c] = dm_ld_cg4(a.x + i);
+			if (i < n) dm_quad_issue(in_t + i, q[c]);
 		}
 #pragma unroll
 		for (int c = 0; c < B; c++) {
 			const int i = i0 + c * (DM_CW * 32 * 4);
 			if (i < n) {
-				ss += xv[c].x * xv[c].x + xv[c].y * xv[c].y + xv[c].z * xv[c].z + xv[c].w * xv[c].w;
-				*reinterpret_cast<float4*>(stash + i) = xv[c];
+				dm_quad_wait(in_t + i, tag, q[c], ab);
+				const float4 x = dm_quad_f4(q[c]);
+				ss += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+				*reinterpret_cast<float4*>(stash + i) = x;
 			}
 		}
 	}
@@ -127,74 +197,107 @@ __device__ __forceinline__ void dm_stage_norm(const MatvecArgs& a, const XqView&
 #pragma unroll
 	for (int i = 0; i < DM_CW; i++) tot += s_red[i];
 	const float scale = 1.0f / sqrtf(tot / (float) n + a.norm_eps); // infer.cpp:229-232
-	for (int i = tid * 4; i < n; i += DM_CW * 32 * 4) { // same elements this thread parked above
+#pragma unroll
+	for (int c = 0; c < DM_GC; c++) { // same elements this thread parked above
+		const int i = tid * 4 + c * (DM_CW * 32 * 4);
+		if (i < n) {
+			const float4 x = *reinterpret_cast<const float4*>(stash + i);
+			const uint4 g = a.norm_type == XALM_F32 ? dm_norm_w4(a, i) : dm_norm_unpack(w.g[c]);
+			float4 o;
+			o.x = x.x * scale * __uint_as_float(g.x); // infer.cpp:233-235
+			o.y = x.y * scale * __uint_as_float(g.y);
+			o.z = x.z * scale * __uint_as_float(g.z);
+			o.w = x.w * scale * __uint_as_float(g.w);
+			xq_store4(v, i, o, lane);
+		}
+	}
+	for (int i = tid * 4 + DM_GC * (DM_CW * 32 * 4); i < n; i += DM_CW * 32 * 4) { // rows longer than 8192
 		const float4 x = *reinterpret_cast<const float4*>(stash + i);
-		const float4 g = dm_norm_w4(a, i);
+		const uint4 g = dm_norm_w4(a, i);
 		float4 o;
-		o.x = x.x * scale * g.x; // infer.cpp:233-235
-		o.y = x.y * scale * g.y;
-		o.z = x.z * scale * g.z;
-		o.w = x.w * scale * g.w;
+		o.x = x.x * scale * __uint_as_float(g.x);
+		o.y = x.y * scale * __uint_as_float(g.y);
+		o.z = x.z * scale * __uint_as_float(g.z);
+		o.w = x.w * scale * __uint_as_float(g.w);
 		xq_store4(v, i, o, lane);
 	}
 }
-
-// ---- activation staging: x (global, written by other SMs) [-> rmsnorm] -> block floating point in shared memory ----------
-template <bool NORM>
-__device__ __forceinline__ void dm_stage(const MatvecArgs& a, uint8_t* xq_base, int xq_cap, float* s_red) {
+__device__ __forceinline__ void dm_stage_plain(const MatvecArgs& a, const dm_tagged* in_t, uint32_t tag, const XqView& v, const DmAbort& ab) {
 	const int n = a.n;
 	const int tid = threadIdx.x, lane = tid & 31;
-	const XqView v = xq_view(xq_base, n);
-	if (NORM) {
-		dm_stage_norm(a, v, s_red, reinterpret_cast<float*>(xq_base + xq_cap) - n); // host: xq_cap >= xq_bytes(n) + 4 n
-	} else {
-		constexpr int B = 4; // loads in flight per thread
-		for (int i0 = tid * 4; i0 < n; i0 += B * DM_CW * 32 * 4) {
-			float4 xv[B];
+	constexpr int B = 8; // chunks in flight per thread: a 7B-class W2 input (14336) takes two trips to L2
+	for (int i0 = tid * 4; i0 < n; i0 += B * DM_CW * 32 * 4) {
+		DmQuad q[B];
 #pragma unroll
-			for (int c = 0; c < B; c++) {
-				const int i = i0 + c * (DM_CW * 32 * 4);
-				if (i < n) xv[c] = dm_ld_cg4(a.x + i);
-			}
+		for (int c = 0; c < B; c++) {
+			const int i = i0 + c * (DM_CW * 32 * 4);
+			if (i < n) dm_quad_issue(in_t + i, q[c]);
+		}
 #pragma unroll
-			for (int c = 0; c < B; c++) {
-				const int i = i0 + c * (DM_CW * 32 * 4);
-				if (i < n) xq_store4(v, i, xv[c], lane);
+		for (int c = 0; c < B; c++) {
+			const int i = i0 + c * (DM_CW * 32 * 4);
+			if (i < n) {
+				dm_quad_wait(in_t + i, tag, q[c], ab);
+				xq_store4(v, i, dm_quad_f4(q[c]), lane);
 			}
 		}
 	}
-	dm_bar();
 }
 
-// ---- attention phase: the 8 consumer warps process (kv head, split) items; same math as attn_decode_kernel (attention.cuh) ----
-// KVDIV = 2 serves 2 x G query heads per kv head as two "virtual" kv heads of G heads each (G = 8 would need > 200 registers per
-// thread; the second pass re-reads the K/V slice from L2).
+// ---- attention phase -----------------------------------------------------------------------------------------------------------
+// Part A: the 8 consumer warps process (kv head, split) items; same math as attn_decode_kernel (attention.cuh).  KVDIV = 2 serves
+// 2 x G query heads per kv head as two "virtual" kv heads of G heads each (G = 8 would need > 200 registers per thread; the
+// second pass re-reads the K/V slice from L2).  Rows written during this token (kv_pos; the re-rotated sinks) come from the
+// tagged side buffers, everything else from the cache.
 template <int HD, int G, int KVDIV>
-__device__ __forceinline__ void dm_attention(const AttnArgs& a, float* scratch, int first, int stride) {
+__device__ __noinline__ void dm_attention(const DmPhase& P, const StepParams& st, float* scratch, int first, int stride, uint32_t tag_in,
+                                             uint32_t tag_out, const DmAbort& ab) {
 	constexpr int NW = DM_CW;
 	constexpr int LPR = HD / 8, RPW = 32 / LPR, TB = 4, NGRP = NW * RPW;
+	const AttnArgs& a = P.at;
 	float* s_m = scratch;                       // [NGRP][G]
 	float* s_l = s_m + NGRP * G;                // [NGRP][G]
 	float* s_scale = s_l + NGRP * G;            // [NGRP][G]
 	float* s_acc = s_scale + NGRP * G;          // [NW][G][HD]
-	__shared__ int s_last;
-	const int kv_len = a.kv_len_fixed >= 0 ? a.kv_len_fixed : a.step->kv_len;
+	const int kv_len = st.kv_len, kv_pos = st.kv_pos, kv_sink = st.kv_sink;
 	const int slen = attn_split_len(kv_len, a.n_splits, a.min_split);
 	const int n_active = (kv_len + slen - 1) / slen;
-	const int n_items = a.n_kv_heads * KVDIV * n_active;
+	const int n_vkv = a.n_kv_heads * KVDIV;
+	const int n_items = n_vkv * n_active;
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int sub = lane / LPR, li = lane % LPR;
 	const int kv_stride = a.n_kv_heads * HD;
+	const int kvd2 = kv_stride / 2;
 	const float inv_sqrt = 1.0f / sqrtf((float) HD);
 	for (int item = first; item < n_items; item += stride) {
 		const int kvh = item / n_active, split = item % n_active; // kvh: virtual kv head (G query heads each)
 		const int kvp = kvh / KVDIV;                              // physical kv head
 		const int t0 = split * slen, t1 = min(kv_len, t0 + slen);
+		const __half* kbase = a.k_cache + (size_t) kvp * HD + li * 8;
+		const __half* vbase = a.v_cache + (size_t) kvp * HD + li * 8;
+		uint4 kq[TB], vq[TB];
+		auto fetch = [&](int tb) {
+#pragma unroll
+			for (int j = 0; j < TB; j++) {
+				const int t = tb + j * RPW + sub;
+				const int tc = t < t1 ? t : t0;
+				kq[j] = __ldcg(reinterpret_cast<const uint4*>(kbase + (size_t) tc * kv_stride));
+				vq[j] = __ldcg(reinterpret_cast<const uint4*>(vbase + (size_t) tc * kv_stride));
+			}
+		};
+		int tb = t0 + warp * RPW * TB;
+		bool have = false;
+		if (tb < t1) { fetch(tb); have = true; } // in flight while q is polled
 		float qf[G][8];
 #pragma unroll
 		for (int g = 0; g < G; g++) {
-			const float* qp = a.q + (size_t) (kvh * G + g) * HD + li * 8;
-			const float4 u = dm_ld_cg4(qp), v = dm_ld_cg4(qp + 4);
+			const dm_tagged* qp = P.in_t + (size_t) (kvh * G + g) * HD + li * 8;
+			DmQuad q0, q1;
+			dm_quad_issue(qp, q0);
+			dm_quad_issue(qp + 4, q1);
+			dm_quad_wait(qp, tag_in, q0, ab);
+			dm_quad_wait(qp + 4, tag_in, q1, ab);
+			const float4 u = dm_quad_f4(q0), v = dm_quad_f4(q1);
 			qf[g][0] = u.x; qf[g][1] = u.y; qf[g][2] = u.z; qf[g][3] = u.w;
 			qf[g][4] = v.x; qf[g][5] = v.y; qf[g][6] = v.z; qf[g][7] = v.w;
 		}
@@ -205,18 +308,27 @@ __device__ __forceinline__ void dm_attention(const AttnArgs& a, float* scratch, 
 #pragma unroll
 			for (int i = 0; i < 8; i++) acc[g][i] = 0.f;
 		}
-		const __half* kbase = a.k_cache + (size_t) kvp * HD + li * 8;
-		const __half* vbase = a.v_cache + (size_t) kvp * HD + li * 8;
-		for (int tb = t0 + warp * RPW * TB; tb < t1; tb += NW * RPW * TB) {
-			uint4 kq[TB], vq[TB];
+		for (; tb < t1; tb += NW * RPW * TB) {
+			if (!have) fetch(tb);
+			have = false;
 			bool ok[TB];
 #pragma unroll
 			for (int j = 0; j < TB; j++) {
 				const int t = tb + j * RPW + sub;
 				ok[j] = t < t1;
-				const int tc = ok[j] ? t : t0;
-				kq[j] = __ldcg(reinterpret_cast<const uint4*>(kbase + (size_t) tc * kv_stride));
-				vq[j] = __ldcg(reinterpret_cast<const uint4*>(vbase + (size_t) tc * kv_stride));
+				if (ok[j] && (t == kv_pos || t < kv_sink)) { // written during this token: take the tagged copy
+					const dm_tagged* kp = (t == kv_pos ? P.tkv : P.tsink + (size_t) t * kvd2) + (kvp * HD + li * 8) / 2;
+					DmQuad q;
+					dm_quad_issue(kp, q);
+					dm_quad_wait(kp, tag_in, q, ab);
+					kq[j] = make_uint4((uint32_t) q.w[0], (uint32_t) q.w[1], (uint32_t) q.w[2], (uint32_t) q.w[3]);
+					if (t == kv_pos) {
+						const dm_tagged* vp = P.tkv + kvd2 + (kvp * HD + li * 8) / 2;
+						dm_quad_issue(vp, q);
+						dm_quad_wait(vp, tag_in, q, ab);
+						vq[j] = make_uint4((uint32_t) q.w[0], (uint32_t) q.w[1], (uint32_t) q.w[2], (uint32_t) q.w[3]);
+					}
+				}
 			}
 			float s[TB][G];
 #pragma unroll
@@ -289,9 +401,9 @@ __device__ __forceinline__ void dm_attention(const AttnArgs& a, float* scratch, 
 			}
 		}
 		dm_bar();
-		const bool single = n_active == 1; // one split: write the normalised output directly, no partial round trip
-		float* pacc = a.part_acc + ((size_t) kvh * a.n_splits + split) * G * HD;
-		float* pml = a.part_ml + ((size_t) kvh * a.n_splits + split) * G * 2;
+		const bool single = n_active == 1; // one split: write the normalised output directly
+		dm_tagged* pacc = P.tpart + ((size_t) kvh * a.n_splits + split) * G * HD;
+		dm_tagged* pml = P.tml + ((size_t) kvh * a.n_splits + split) * G * 2;
 		for (int i = threadIdx.x; i < G * HD; i += NW * 32) {
 			const int g = i / HD, dpos = i % HD;
 			float v = 0.f;
@@ -300,53 +412,93 @@ __device__ __forceinline__ void dm_attention(const AttnArgs& a, float* scratch, 
 			if (single) {
 				float L = 0.f;
 				for (int k = 0; k < NGRP; k++) L += s_l[k * G + g] * s_scale[k * G + g];
-				a.out[(size_t) kvh * G * HD + i] = v / L;
+				const float o = v / L;
+				dm_st(P.out_t + (size_t) kvh * G * HD + i, dm_packf(o, tag_out));
+				a.out[(size_t) kvh * G * HD + i] = o;
 			} else {
-				pacc[i] = v;
+				dm_st(pacc + i, dm_packf(v, tag_out));
 			}
 		}
 		if (!single && threadIdx.x < G) {
 			const int g = threadIdx.x;
 			float L = 0.f, M = -CUDART_INF_F;
 			for (int k = 0; k < NGRP; k++) { L += s_l[k * G + g] * s_scale[k * G + g]; M = fmaxf(M, s_m[k * G + g]); }
-			pml[2 * g] = M;
-			pml[2 * g + 1] = L;
+			dm_st2(pml + 2 * g, dm_packf(M, tag_out), dm_packf(L, tag_out));
 		}
-		if (!single) {
-			__threadfence();
-			dm_bar();
-			if (threadIdx.x == 0) {
-				const unsigned int ticket = atomicAdd(&a.tickets[kvh], 1u);
-				s_last = ticket == (unsigned int) (n_active - 1);
-				if (s_last) a.tickets[kvh] = 0;
-			}
-			dm_bar();
-			if (s_last) { // the last split of this kv head to finish merges all of them, in split order
-				__threadfence();
-				const float* bacc = a.part_acc + (size_t) kvh * a.n_splits * G * HD;
-				const float* bml = a.part_ml + (size_t) kvh * a.n_splits * G * 2;
-				for (int i = threadIdx.x; i < G * HD; i += NW * 32) {
-					const int g = i / HD;
-					float mm = -CUDART_INF_F;
-					for (int sidx = 0; sidx < n_active; sidx++) mm = fmaxf(mm, __ldcg(bml + ((size_t) sidx * G + g) * 2));
-					float num = 0.f, den = 0.f;
-					for (int sidx = 0; sidx < n_active; sidx++) {
-						const float ms = __ldcg(bml + ((size_t) sidx * G + g) * 2), ls = __ldcg(bml + ((size_t) sidx * G + g) * 2 + 1);
-						const float sc = expf(ms - mm);
-						num += sc * __ldcg(bacc + (size_t) sidx * G * HD + i);
-						den += sc * ls;
-					}
-					a.out[(size_t) kvh * G * HD + i] = num / den;
+		dm_bar(); // scratch reuse by the next item / the merge
+	}
+	// ---- Part B: distributed merge of the splits — CTA c merges outputs [32c, 32c + 32) (one head slice), in split order ----
+	if (n_active > 1) {
+		const int n_out = n_vkv * G * HD;
+		float* s_ms = scratch;                    // [DM_MAX_SPLITS] split maxima of this head
+		float* s_num = scratch + DM_MAX_SPLITS;   // [8][32]
+		float* s_den = s_num + 8 * 32;            // [8]
+		const int ol = threadIdx.x & 31, sg = threadIdx.x >> 5;
+		for (int c = (int) blockIdx.x; c * 32 < n_out; c += (int) gridDim.x) {
+			const int o = c * 32 + ol;
+			const int h = o / HD, d = o % HD, kvh = h / G, g = h % G;
+			constexpr int MS = DM_MAX_SPLITS / 8;
+			dm_tagged wv[MS], wm[MS], wl[MS];
+#pragma unroll
+			for (int i = 0; i < MS; i++) {
+				const int sp = sg + 8 * i;
+				if (sp < n_active) {
+					const size_t base = ((size_t) kvh * a.n_splits + sp) * G + g;
+					wv[i] = dm_ld(P.tpart + base * HD + d);
+					dm_ld2(P.tml + base * 2, wm[i], wl[i]);
 				}
 			}
+			float mv[MS], lv[MS], vv[MS];
+#pragma unroll
+			for (int i = 0; i < MS; i++) {
+				const int sp = sg + 8 * i;
+				mv[i] = -CUDART_INF_F; lv[i] = 0.f; vv[i] = 0.f;
+				if (sp < n_active) {
+					const size_t base = ((size_t) kvh * a.n_splits + sp) * G + g;
+					unsigned int spins = 0;
+					while (!(dm_fresh(wv[i], tag_out) && dm_fresh(wm[i], tag_out) && dm_fresh(wl[i], tag_out))) {
+						if ((++spins & 63u) == 0 && dm_check_abort(ab, spins)) break;
+						wv[i] = dm_ld(P.tpart + base * HD + d);
+						dm_ld2(P.tml + base * 2, wm[i], wl[i]);
+					}
+					vv[i] = __uint_as_float((uint32_t) wv[i]);
+					mv[i] = __uint_as_float((uint32_t) wm[i]);
+					lv[i] = __uint_as_float((uint32_t) wl[i]);
+					if (ol == 0) s_ms[sp] = mv[i];
+				}
+			}
+			dm_bar();
+			float M = -CUDART_INF_F;
+			for (int sp = 0; sp < n_active; sp++) M = fmaxf(M, s_ms[sp]);
+			float num = 0.f, den = 0.f;
+#pragma unroll
+			for (int i = 0; i < MS; i++) {
+				if (sg + 8 * i < n_active) {
+					const float sc = expf(mv[i] - M);
+					num += sc * vv[i];
+					den += sc * lv[i];
+				}
+			}
+			s_num[sg * 32 + ol] = num;
+			if (ol == 0) s_den[sg] = den;
+			dm_bar();
+			if (sg == 0) {
+				float tn = 0.f, td = 0.f;
+#pragma unroll
+				for (int k = 0; k < 8; k++) { tn += s_num[k * 32 + ol]; td += s_den[k]; }
+				const float r = tn / td;
+				dm_st(P.out_t + o, dm_packf(r, tag_out));
+				a.out[o] = r;
+			}
+			dm_bar();
 		}
-		dm_bar(); // scratch reuse by the next item
 	}
 }
 template <int G, int KVDIV>
-__device__ __forceinline__ void dm_attention_hd(const AttnArgs& a, int HD, float* scratch, int first, int stride) {
-	if (HD == 64) dm_attention<64, G, KVDIV>(a, scratch, first, stride);
-	else dm_attention<128, G, KVDIV>(a, scratch, first, stride);
+__device__ __forceinline__ void dm_attention_hd(const DmPhase& P, const StepParams& st, float* scratch, int first, int stride, uint32_t tag_in,
+                                                uint32_t tag_out, const DmAbort& ab) {
+	if (P.HD == 64) dm_attention<64, G, KVDIV>(P, st, scratch, first, stride, tag_in, tag_out, ab);
+	else dm_attention<128, G, KVDIV>(P, st, scratch, first, stride, tag_in, tag_out, ab);
 }
 
 template <int TYPE>
@@ -354,6 +506,8 @@ __global__ void __launch_bounds__(DM_THREADS, 1) decode_token_kernel(const DmArg
 	using F = IdpFmt<TYPE>;
 	constexpr int KW = DM_KW, R = DM_R, RC = DM_RC, U = DM_U, UB = F::UB;
 	constexpr int ROW_STAGE = U * UB; // bytes of one row inside a ring slot
+	constexpr int PH_WORDS = (int) (sizeof(DmPhase) / 4);
+	static_assert(sizeof(DmPhase) % 4 == 0 && PH_WORDS <= DM_CW * 32, "one descriptor word per consumer thread");
 	const int NS = mk.NS;
 	const int G = (int) gridDim.x;
 
@@ -364,7 +518,9 @@ __global__ void __launch_bounds__(DM_THREADS, 1) decode_token_kernel(const DmArg
 	float* s_red = part + 2 * KW * RC;                                           // [16]
 	uint64_t* full = reinterpret_cast<uint64_t*>(s_red + 16);
 	uint64_t* empty = full + NS;
-	__shared__ MatvecArgs s_a; // this phase's arguments (the epilogue reads a dozen fields per tile)
+	__shared__ __align__(16) DmPhase s_ph[2]; // this phase's descriptor and the next one's (fetched a phase ahead)
+	__shared__ StepParams s_step;
+	__shared__ float s_freq[DM_MAX_HD / 2];
 	__shared__ int s_abort;
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -376,20 +532,35 @@ __global__ void __launch_bounds__(DM_THREADS, 1) decode_token_kernel(const DmArg
 		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
+	if (threadIdx.x < PH_WORDS) reinterpret_cast<uint32_t*>(&s_ph[0])[threadIdx.x] = reinterpret_cast<const uint32_t*>(&mk.phases[0])[threadIdx.x];
+	if (threadIdx.x < (int) (sizeof(StepParams) / 4)) reinterpret_cast<uint32_t*>(&s_step)[threadIdx.x] = reinterpret_cast<const uint32_t*>(mk.step)[threadIdx.x];
+	if (threadIdx.x < mk.head_dim / 2) s_freq[threadIdx.x] = mk.rope_freq[threadIdx.x];
 	__syncthreads();
 
 	if (warp == DM_CW) {
-		// ===================== producer: the whole token's weight stream, never blocked by a hand-off =====================
+		// ===================== producer: the whole token's weight stream, never blocked by anybody =====================
 		if (lane == 0) {
 			int slot = 0, phase = 0;
 			for (int ph = 0; ph < mk.n_phases; ph++) {
 				const DmPhase& P = mk.phases[ph];
+				for (int k = ph + 2; k <= ph + 3 && k < mk.n_phases; k++) { // descriptors two and three phases ahead -> L2
+					const char* d = reinterpret_cast<const char*>(&mk.phases[k]);
+					for (int o = 0; o < (int) sizeof(DmPhase); o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(d + o));
+				}
 				if (P.kind != DM_MATVEC) continue;
 				const int nu = P.a.n / 256, n_tiles = P.n_tiles, kranges = P.kranges;
 				const int epi = P.a.epi, glu_off = P.a.glu_off;
 				const uint8_t* w0 = P.a.w.p0;
 				const size_t ws = P.a.w.s0;
 				const int first = ((int) blockIdx.x + G - P.tile_off % G) % G;
+				if (epi == EPI_QKV && ph + 1 < mk.n_phases && mk.phases[ph + 1].kind == DM_ATTN) {
+					// the K/V rows the attention phase after this one will walk: this CTA pulls its share into L2 now, so that phase
+					// reads them at L2 latency instead of queueing behind the weight stream in DRAM
+					const AttnArgs& at = mk.phases[ph + 1].at;
+					const unsigned long long kvb = (unsigned long long) s_step.kv_len * at.n_kv_heads * mk.phases[ph + 1].HD * sizeof(__half);
+					l2_prefetch_slice(reinterpret_cast<const uint8_t*>(at.k_cache), kvb, (int) blockIdx.x, G);
+					l2_prefetch_slice(reinterpret_cast<const uint8_t*>(at.v_cache), kvb, (int) blockIdx.x, G);
+				}
 				for (int tile = first; tile < n_tiles; tile += G) {
 					const int row0 = tile * RC;
 					for (int kr = 0; kr < kranges; kr++) {
@@ -420,118 +591,151 @@ __global__ void __launch_bounds__(DM_THREADS, 1) decode_token_kernel(const DmArg
 	const int kw = warp % KW, rw = warp / KW;
 	const int hA = (lane >> 2) & 1;
 	int slot = 0, phase = 0;
+	const DmAbort ab = {&s_abort, mk.gbar + 1, mk.err};
+	const uint32_t tagbase = s_step.ar_base;
 	unsigned long long* tl = (mk.tl && blockIdx.x == 0 && threadIdx.x == 0) ? mk.tl : nullptr;
 
 	for (int ph = 0; ph < mk.n_phases; ph++) {
-		const DmPhase& P = mk.phases[ph];
+		const DmPhase& P = s_ph[ph & 1];
 		if (tl) tl[4 * ph] = gtime();
 		if (mk.tl && threadIdx.x == 0) mk.tl[(size_t) 4 * mk.tl_phases + (size_t) ph * G + blockIdx.x] = gtime();
-		if (ph > 0) dm_handoff(mk.gbar, (unsigned int) ph * (unsigned int) G, mk.err, &s_abort);
-		if (tl) tl[4 * ph + 1] = gtime();
+		// the next phase's descriptor travels while this phase runs (read once per token: DRAM, or L2 thanks to the producer)
+		uint32_t next_word = 0;
+		const bool has_next = ph + 1 < mk.n_phases && threadIdx.x < PH_WORDS;
+		if (has_next) next_word = reinterpret_cast<const uint32_t*>(&mk.phases[ph + 1])[threadIdx.x];
+		const uint32_t tag_in = tagbase + (uint32_t) ph + 1u, tag_out = tagbase + (uint32_t) ph + 2u;
 		const int first = ((int) blockIdx.x + G - P.tile_off % G) % G;
 		if (P.kind == DM_ATTN) {
 			float* scratch = reinterpret_cast<float*>(xq_base);
 			switch (P.G) {
-				case 1: dm_attention_hd<1, 1>(P.at, P.HD, scratch, first, G); break;
-				case 2: dm_attention_hd<2, 1>(P.at, P.HD, scratch, first, G); break;
-				case 4: dm_attention_hd<4, 1>(P.at, P.HD, scratch, first, G); break;
-				case 8: dm_attention_hd<4, 2>(P.at, P.HD, scratch, first, G); break;
+				case 1: dm_attention_hd<1, 1>(P, s_step, scratch, first, G, tag_in, tag_out, ab); break;
+				case 2: dm_attention_hd<2, 1>(P, s_step, scratch, first, G, tag_in, tag_out, ab); break;
+				case 4: dm_attention_hd<4, 1>(P, s_step, scratch, first, G, tag_in, tag_out, ab); break;
+				case 8: dm_attention_hd<4, 2>(P, s_step, scratch, first, G, tag_in, tag_out, ab); break;
 			}
-			if (tl) { tl[4 * ph + 2] = tl[4 * ph + 1]; tl[4 * ph + 3] = gtime(); }
-			continue;
-		}
-		// this phase's arguments -> shared memory
-		{
-			const uint32_t* src = reinterpret_cast<const uint32_t*>(&P.a);
-			uint32_t* dst = reinterpret_cast<uint32_t*>(&s_a);
-			for (int i = threadIdx.x; i < (int) (sizeof(MatvecArgs) / 4); i += DM_CW * 32) dst[i] = src[i];
-		}
-		dm_bar();
-		const MatvecArgs& a = s_a;
-		const int n = a.n, nu = n / 256, epi = a.epi;
-		float* const out = a.out;
-		if (epi == EPI_QKV && blockIdx.x == 0 && a.step->kv_sink > 0) { // attention sinks move on by one position (infer.cpp:416-431)
-			const int pairs = a.kv_dim / 2;
-			for (int i = threadIdx.x; i < a.step->kv_sink * pairs; i += DM_CW * 32) {
-				const int r = i / pairs, p = i % pairs;
-				__half2* kp = reinterpret_cast<__half2*>(a.k_cache + (size_t) r * a.kv_dim) + p;
-				float2 vv = __half22float2(__ldcg(kp));
-				rope_pair(vv.x, vv.y, (2 * p) % a.head_dim, 1, a.rope_freq);
-				*kp = __floats2half2_rn(vv.x, vv.y);
+			if (tl) { tl[4 * ph + 1] = tl[4 * ph + 2] = tl[4 * ph]; tl[4 * ph + 3] = gtime(); }
+		} else {
+			const MatvecArgs& a = P.a;
+			const int n = a.n, nu = n / 256, epi = a.epi;
+			const int kranges = P.kranges, n_tiles = P.n_tiles;
+			dm_tagged* const out_t = P.out_t;
+			if (epi == EPI_QKV && blockIdx.x == 0 && s_step.kv_sink > 0) { // attention sinks move on by one position (infer.cpp:416-431)
+				const int pairs = a.kv_dim / 2;
+				for (int i = threadIdx.x; i < s_step.kv_sink * pairs; i += DM_CW * 32) {
+					const int r = i / pairs, p = i % pairs;
+					__half2* kp = reinterpret_cast<__half2*>(a.k_cache + (size_t) r * a.kv_dim) + p;
+					float2 vv = __half22float2(__ldcg(kp));
+					rope_pair(vv.x, vv.y, (2 * p) % a.head_dim, 1, s_freq);
+					const __half2 h2 = __floats2half2_rn(vv.x, vv.y);
+					*kp = h2;
+					dm_st(P.tsink + (size_t) r * pairs + p, dm_pack(*reinterpret_cast<const uint32_t*>(&h2), tag_out));
+				}
 			}
-		}
-		if (a.norm_w != nullptr) dm_stage<true>(a, xq_base, mk.xq_cap, s_red);
-		else dm_stage<false>(a, xq_base, mk.xq_cap, s_red);
-		if (tl) tl[4 * ph + 2] = gtime();
-		const XqView xv = xq_view(xq_base, n);
+			if (first < n_tiles) { // a CTA without tiles in this phase reads nothing (and so can never wait for an overwritten tag)
+				const XqView xv = xq_view(xq_base, n);
+				if (a.norm_w != nullptr) {
+					DmNormW nw;
+					dm_norm_fetch(a, nw);
+					dm_stage_norm(a, P.in_t, tag_in, xv, s_red, reinterpret_cast<float*>(xq_base + mk.xq_cap) - n, nw, ab); // host: xq_cap >= xq_bytes(n) + 4 n
+				} else {
+					dm_stage_plain(a, P.in_t, tag_in, xv, ab);
+				}
+				dm_bar();
+				if (tl) tl[4 * ph + 1] = tl[4 * ph + 2] = gtime();
 
-		const int kranges = P.kranges, n_tiles = P.n_tiles;
-		int tcount = 0;
-		for (int tile = first; tile < n_tiles; tile += G, tcount++) {
-			const int row0 = tile * RC;
-			const bool reducer = warp == (tcount % DM_CW);
-			// residual: fetch the old activation early so the epilogue does not sit on an L2 round trip
-			float xold = 0.f;
-			if (epi == EPI_RESIDUAL && reducer && lane < RC) xold = __ldcg(out + row0 + lane);
-			float y[R];
+				int tcount = 0;
+				for (int tile = first; tile < n_tiles; tile += G, tcount++) {
+					const int row0 = tile * RC;
+					const bool reducer = warp == (tcount % DM_CW);
+					// residual: request the old activation early so the epilogue does not sit on a trip to L2
+					dm_tagged xold_w = 0;
+					if (epi == EPI_RESIDUAL && reducer && lane < RC) xold_w = dm_ld(out_t + row0 + lane);
+					float y[R];
 #pragma unroll
-			for (int r = 0; r < R; r++) y[r] = 0.f;
-			for (int kr = 0; kr < kranges; kr++) {
-				const int u0 = kr * U;
-				const int nb = 8 * min(U, nu - u0); // blocks per row in this stage
-				const int b = kw * 32 + lane;
-				const bool got = dm_mbar_wait(&full[slot], phase, &s_abort);
-				if (got && b < nb) {
-					XqBlock xb;
-					xq_load(xv, u0 * 8 + b, hA, xb);
-					const uint8_t* unit = ring + (size_t) slot * mk.slot_bytes + (size_t) (rw * R) * ROW_STAGE + (size_t) (b >> 3) * UB;
+					for (int r = 0; r < R; r++) y[r] = 0.f;
+					for (int kr = 0; kr < kranges; kr++) {
+						const int u0 = kr * U;
+						const int nb = 8 * min(U, nu - u0); // blocks per row in this stage
+						const int b = kw * 32 + lane;
+						const bool got = dm_mbar_wait(&full[slot], phase, &s_abort);
+						if (got && b < nb) {
+							XqBlock xb;
+							xq_load(xv, u0 * 8 + b, hA, xb);
+							const uint8_t* unit = ring + (size_t) slot * mk.slot_bytes + (size_t) (rw * R) * ROW_STAGE + (size_t) (b >> 3) * UB;
 #pragma unroll
-					for (int r = 0; r < R; r++) F::block(unit + (size_t) r * ROW_STAGE, b & 7, hA, xb, y[r]);
-				}
-				__syncwarp();
-				if (lane == 0) mbar_arrive(&empty[slot]);
-				if (++slot == NS) { slot = 0; phase ^= 1; }
-			}
-			// ---- lanes -> one sum per row (transposed butterfly: 6 shuffles for 4 rows), K-slices -> shared memory (fixed order) ----
-			{
-				const bool b4 = lane & 16, b3 = lane & 8;
-				float k0 = b4 ? y[2] : y[0], k1 = b4 ? y[3] : y[1];
-				const float s0 = b4 ? y[0] : y[2], s1 = b4 ? y[1] : y[3];
-				k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
-				k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-				float k = b3 ? k1 : k0;
-				const float s = b3 ? k0 : k1;
-				k += __shfl_xor_sync(0xffffffffu, s, 8);
-				k += __shfl_xor_sync(0xffffffffu, k, 4);
-				k += __shfl_xor_sync(0xffffffffu, k, 2);
-				k += __shfl_xor_sync(0xffffffffu, k, 1);
-				if ((lane & 7) == 0) part[(tcount & 1) * (KW * RC) + kw * RC + rw * R + (b4 ? 2 : 0) + (b3 ? 1 : 0)] = k;
-			}
-			dm_bar();
-			if (reducer) { // rotating reducer warp: lane i owns row i of the tile
-				const float* pt = part + (tcount & 1) * (KW * RC);
-				float yv = 0.f;
-				if (lane < RC) {
-#pragma unroll
-					for (int k = 0; k < KW; k++) yv += pt[k * RC + lane];
-				}
-				const float ynext = __shfl_down_sync(0xffffffffu, yv, 1);
-				if (lane < RC) {
-					if (epi == EPI_RESIDUAL) {
-						out[row0 + lane] = xold + yv; // infer.cpp:450-452, :492-494
-					} else if (epi == EPI_GLU) {
-						if ((lane & 1) == 0) { // (W1[o], W3[o]) sit in adjacent rows of a GLU tile
-							const float g = a.act == XALM_SILU ? act_silu(yv) : act_gelu(yv);
-							out[(row0 + lane) >> 1] = g * ynext; // infer.cpp:470-488
+							for (int r = 0; r < R; r++) F::block(unit + (size_t) r * ROW_STAGE, b & 7, hA, xb, y[r]);
 						}
-					} else if ((lane & 1) == 0) {
-						const float y2[2] = {yv, ynext};
-						epilogue<2>(a, row0 + lane, y2);
+						__syncwarp();
+						if (lane == 0) mbar_arrive(&empty[slot]);
+						if (++slot == NS) { slot = 0; phase ^= 1; }
+					}
+					// ---- lanes -> one sum per row (transposed butterfly: 6 shuffles for 4 rows), K-slices -> shared memory (fixed order) ----
+					{
+						const bool b4 = lane & 16, b3 = lane & 8;
+						float k0 = b4 ? y[2] : y[0], k1 = b4 ? y[3] : y[1];
+						const float s0 = b4 ? y[0] : y[2], s1 = b4 ? y[1] : y[3];
+						k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+						k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+						float k = b3 ? k1 : k0;
+						const float s = b3 ? k0 : k1;
+						k += __shfl_xor_sync(0xffffffffu, s, 8);
+						k += __shfl_xor_sync(0xffffffffu, k, 4);
+						k += __shfl_xor_sync(0xffffffffu, k, 2);
+						k += __shfl_xor_sync(0xffffffffu, k, 1);
+						if ((lane & 7) == 0) part[(tcount & 1) * (KW * RC) + kw * RC + rw * R + (b4 ? 2 : 0) + (b3 ? 1 : 0)] = k;
+					}
+					dm_bar();
+					if (reducer) { // rotating reducer warp: lane i owns row i of the tile
+						const float* pt = part + (tcount & 1) * (KW * RC);
+						float yv = 0.f;
+						if (lane < RC) {
+#pragma unroll
+							for (int k = 0; k < KW; k++) yv += pt[k * RC + lane];
+						}
+						const float ynext = __shfl_down_sync(0xffffffffu, yv, 1);
+						const int row = row0 + lane;
+						if (lane < RC) {
+							if (epi == EPI_RESIDUAL) {
+								const float xn = __uint_as_float((uint32_t) xold_w) + yv; // infer.cpp:450-452, :492-494
+								dm_st(out_t + row, dm_packf(xn, tag_out));
+								a.out[row] = xn;
+							} else if (epi == EPI_GLU) {
+								if ((lane & 1) == 0) { // (W1[o], W3[o]) sit in adjacent rows of a GLU tile
+									const float g = a.act == XALM_SILU ? act_silu(yv) : act_gelu(yv);
+									const float hv = g * ynext; // infer.cpp:470-488
+									dm_st(out_t + (row >> 1), dm_packf(hv, tag_out));
+									a.out[row >> 1] = hv;
+								}
+							} else if (epi == EPI_STORE) {
+								if (row < a.d) a.out[row] = yv; // logits (infer.cpp:637)
+							} else if ((lane & 1) == 0) { // EPI_QKV: clip -> RoPE -> q, or fp16 K/V into the cache ring (infer.cpp:388-414)
+								float v0 = clipf(yv, a.qkv_clip), v1 = clipf(ynext, a.qkv_clip);
+								if (row < a.q_dim) {
+									rope_pair(v0, v1, row % a.head_dim, s_step.pos, s_freq);
+									dm_st2(out_t + row, dm_packf(v0, tag_out), dm_packf(v1, tag_out));
+									a.out[row] = v0;
+									a.out[row + 1] = v1;
+								} else if (row < a.q_dim + a.kv_dim) {
+									const int i = row - a.q_dim;
+									rope_pair(v0, v1, i % a.head_dim, s_step.pos, s_freq);
+									const __half2 h2 = __floats2half2_rn(v0, v1);
+									*reinterpret_cast<__half2*>(a.k_cache + (size_t) s_step.kv_pos * a.kv_dim + i) = h2;
+									dm_st(P.tkv + i / 2, dm_pack(*reinterpret_cast<const uint32_t*>(&h2), tag_out));
+								} else {
+									const int i = row - a.q_dim - a.kv_dim;
+									const __half2 h2 = __floats2half2_rn(v0, v1);
+									*reinterpret_cast<__half2*>(a.v_cache + (size_t) s_step.kv_pos * a.kv_dim + i) = h2;
+									dm_st(P.tkv + a.kv_dim / 2 + i / 2, dm_pack(*reinterpret_cast<const uint32_t*>(&h2), tag_out));
+								}
+							}
+						}
 					}
 				}
 			}
+			if (tl) tl[4 * ph + 3] = gtime();
 		}
-		if (tl) tl[4 * ph + 3] = gtime();
+		if (has_next) reinterpret_cast<uint32_t*>(&s_ph[(ph + 1) & 1])[threadIdx.x] = next_word;
+		dm_bar(); // every warp is done with this phase's staged activations, partial sums and descriptor
 	}
 	if (threadIdx.x == 0 && s_abort && mk.err) *mk.err = 3u;
 }

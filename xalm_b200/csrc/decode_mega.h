@@ -7,16 +7,28 @@ namespace xalm {
 
 enum { DM_MATVEC = 0, DM_ATTN = 1 };
 
+// A "tagged" vector: one 64-bit word per element, {value bits (low), tag (high)}, written with a single 8-byte store.  The
+// consumer polls the words it needs until they carry the producing phase's tag: the hand-off between phases IS the data —
+// no fence, no flag, no counter, one trip through L2.  Tag of phase k of a token = StepParams.ar_base + k + 2 (embedding: + 1).
+typedef unsigned long long dm_tagged;
+
 // One phase of a token: a fused matvec (norm+QKV+rope+KV, Wo+residual, norm+W1|W3+GLU, W2+residual, norm+classifier) or the
-// decode attention of a layer.  Phases run in order on the same resident CTAs, separated by a grid-wide hand-off.
+// decode attention of a layer.  Phases run in order on the same resident CTAs.
 struct DmPhase {
 	int kind;
 	int n_tiles;   // matvec: virtual rows / 8
 	int kranges;   // matvec: ring stages per tile
 	int tile_off;  // matvec/attention: work item t runs on CTA (t + tile_off) % grid (rotated so the odd item moves around)
-	MatvecArgs a;
-	AttnArgs at;
-	int G, HD;
+	MatvecArgs a;  // matvec: weights, epilogue kind, norm weights, KV cache rows, plain outputs (x, logits)
+	AttnArgs at;   // attention: cache pointers, split geometry
+	int G, HD;     // attention: query heads per kv head, head dim
+	// tagged vectors
+	const dm_tagged* in_t;  // matvec input (x, xb2 or hb); attention: q
+	dm_tagged* out_t;       // matvec output: x (residual: read-modify-write), hb (GLU), q (QKV); attention: xb2
+	dm_tagged* tkv;         // QKV / attention: this token's K then V row as {half2 bits, tag}, (2, kv_dim / 2)
+	dm_tagged* tsink;       // QKV / attention: the re-rotated sink K rows, (KV_SINKS, kv_dim / 2)
+	dm_tagged* tpart;       // attention: per-split partial outputs (n_vkv, n_splits, G', HD)
+	dm_tagged* tml;         // attention: per-split (max, sum) pairs (n_vkv, n_splits, G', 2)
 };
 
 struct DmArgs {
@@ -25,9 +37,12 @@ struct DmArgs {
 	int NS;                     // ring slots
 	int slot_bytes;             // 8 rows x 16 units
 	int xq_cap;                 // bytes reserved for the staged activations / attention scratch
-	unsigned int* gbar;         // hand-off counter, zero at launch
-	unsigned int* err;          // pinned host word: set when a hand-off wait gives up
-	unsigned long long* tl;     // optional timeline: tl_phases x 4 stamps of CTA 0, then tl_phases x grid arrival stamps (or nullptr)
+	unsigned int* gbar;         // [1] = device-wide abort word, zero at launch
+	unsigned int* err;          // pinned host word: set when a wait gives up
+	const StepParams* step;     // this token's scalars
+	const float* rope_freq;     // (head_dim / 2,)
+	int head_dim;
+	unsigned long long* tl;     // optional timeline: tl_phases x 4 stamps of CTA 0, then tl_phases x grid phase-entry stamps (or nullptr)
 	int tl_phases;              // phases the timeline buffer was sized for
 };
 
@@ -36,6 +51,8 @@ constexpr int DM_THREADS = (DM_CW + 1) * 32;   // + one producer warp
 constexpr int DM_KW = 4, DM_RW = 2, DM_R = 4;  // K-slice warps x row groups, rows per warp
 constexpr int DM_RC = DM_RW * DM_R;            // rows per tile
 constexpr int DM_U = 16;                       // units (of 256 elements) per ring stage
+constexpr int DM_MAX_SPLITS = 32;              // attention splits per kv head the distributed merge takes
+constexpr int DM_MAX_HD = 128;
 
 bool dm_supported_type(int type);
 size_t dm_attn_scratch_bytes(int HD, int G);
