@@ -173,7 +173,7 @@ int xalm_cuda_tune(const char* key, int value);
  * %globaltimer (ns) of block 0 at entry, after the dependency wait, at exit. */
 int xalm_cuda_timeline(int n_records, unsigned long long* out, int* n_out);
 /* Same idea for the one-kernel-per-token decode path (decode_mega.cu; tune "mega_timeline" = 1 before the first forward):
- * out receives n_phases x 4 u64 of CTA 0 (arrival at the hand-off, hand-off done, activations staged, phase done) followed by
+ * out receives n_phases x 8 u64 of CTA 0 (phase entry, hand-off done, activations staged, phase done, four finer marks) followed by
  * n_phases x grid arrival stamps of every CTA.  With out == NULL only n_phases / grid are returned (0 = token kernel not in use). */
 int xalm_cuda_mega_timeline(xalm_cuda_model* m, unsigned long long* out, size_t cap_words, int* n_phases, int* grid);
 

@@ -82,14 +82,16 @@ def perf(shape, wtname, layers=None):
                 agg = {}
                 for ph in range(nph):
                     nm = names[ph % 5] if ph < nph - 1 else "cls"
-                    a, b, c, d = t4[ph]
+                    a, b, c, d = t4[ph][:4]
                     skew = (arr[ph].max() - arr[ph].min()) / 1e3
-                    agg.setdefault(nm, []).append(((b - a) / 1e3, (c - b) / 1e3, (d - c) / 1e3, skew))
+                    ex = [(int(t4[ph][k]) - int(a)) / 1e3 if t4[ph][k] else -1.0 for k in (4, 5, 6, 7)]
+                    agg.setdefault(nm, []).append(((b - a) / 1e3, (c - b) / 1e3, (d - c) / 1e3, skew, *ex))
                 tot = (t4[-1, 3] - t4[0, 0]) / 1e3
                 print(f"   token kernel at pos 4000: {tot:.1f} us total (CTA 0); per phase kind: mean us of [hand-off wait, staging, tiles] and arrival skew over CTAs")
                 for nm, v in agg.items():
                     v = np.array(v)
-                    print(f"     {nm:5s} n={len(v):3d} handoff {v[:,0].mean():6.2f}  stage {v[:,1].mean():6.2f}  tiles {v[:,2].mean():6.2f}  skew {v[:,3].mean():6.2f}")
+                    print(f"     {nm:5s} n={len(v):3d} handoff {v[:,0].mean():6.2f}  stage {v[:,1].mean():6.2f}  tiles {v[:,2].mean():6.2f}  skew {v[:,3].mean():6.2f}"
+                          f"   marks since phase entry: {v[:,4].mean():6.2f} {v[:,5].mean():6.2f} {v[:,6].mean():6.2f} {v[:,7].mean():6.2f}")
         model.close()
     capi.tune("mega", 1); capi.tune("mega_timeline", 0)
 

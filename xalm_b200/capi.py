@@ -180,16 +180,16 @@ def timeline_stop(n_records: int) -> np.ndarray:
 
 
 def mega_timeline(handle):
-    """(stamps of CTA 0 [n_phases, 4], arrival stamps of every CTA [n_phases, grid]) of the last token kernel, in ns;
+    """(stamps of CTA 0 [n_phases, 8], arrival stamps of every CTA [n_phases, grid]) of the last token kernel, in ns;
     (None, None) when the one-kernel-per-token path is not in use.  Needs tune("mega_timeline", 1) before the first forward."""
     n_ph, grid = C.c_int(0), C.c_int(0)
     check(lib().xalm_cuda_mega_timeline(handle, None, 0, C.byref(n_ph), C.byref(grid)))
     if not n_ph.value:
         return None, None
-    words = n_ph.value * (4 + grid.value)
+    words = n_ph.value * (8 + grid.value)
     out = np.zeros(words, dtype=np.uint64)
     check(lib().xalm_cuda_mega_timeline(handle, _p(out), words, C.byref(n_ph), C.byref(grid)))
-    return out[: 4 * n_ph.value].reshape(n_ph.value, 4), out[4 * n_ph.value:].reshape(n_ph.value, grid.value)
+    return out[: 8 * n_ph.value].reshape(n_ph.value, 8), out[8 * n_ph.value:].reshape(n_ph.value, grid.value)
 
 
 def bench_matvec(type_id: int, n: int, d: int, n_buffers: int, iters: int, epi: int = 0, with_norm: bool = False) -> float:

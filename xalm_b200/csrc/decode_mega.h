@@ -7,11 +7,6 @@ namespace xalm {
 
 enum { DM_MATVEC = 0, DM_ATTN = 1 };
 
-// A "tagged" vector: one 64-bit word per element, {value bits (low), tag (high)}, written with a single 8-byte store.  The
-// consumer polls the words it needs until they carry the producing phase's tag: the hand-off between phases IS the data —
-// no fence, no flag, no counter, one trip through L2.  Tag of phase k of a token = StepParams.ar_base + k + 2 (embedding: + 1).
-typedef unsigned long long dm_tagged;
-
 // One phase of a token: a fused matvec (norm+QKV+rope+KV, Wo+residual, norm+W1|W3+GLU, W2+residual, norm+classifier) or the
 // decode attention of a layer.  Phases run in order on the same resident CTAs.
 struct DmPhase {
@@ -22,13 +17,6 @@ struct DmPhase {
 	MatvecArgs a;  // matvec: weights, epilogue kind, norm weights, KV cache rows, plain outputs (x, logits)
 	AttnArgs at;   // attention: cache pointers, split geometry
 	int G, HD;     // attention: query heads per kv head, head dim
-	// tagged vectors
-	const dm_tagged* in_t;  // matvec input (x, xb2 or hb); attention: q
-	dm_tagged* out_t;       // matvec output: x (residual: read-modify-write), hb (GLU), q (QKV); attention: xb2
-	dm_tagged* tkv;         // QKV / attention: this token's K then V row as {half2 bits, tag}, (2, kv_dim / 2)
-	dm_tagged* tsink;       // QKV / attention: the re-rotated sink K rows, (KV_SINKS, kv_dim / 2)
-	dm_tagged* tpart;       // attention: per-split partial outputs (n_vkv, n_splits, G', HD)
-	dm_tagged* tml;         // attention: per-split (max, sum) pairs (n_vkv, n_splits, G', 2)
 };
 
 struct DmArgs {
@@ -37,7 +25,7 @@ struct DmArgs {
 	int NS;                     // ring slots
 	int slot_bytes;             // 8 rows x 16 units
 	int xq_cap;                 // bytes reserved for the staged activations / attention scratch
-	unsigned int* gbar;         // [1] = device-wide abort word, zero at launch
+	unsigned int* gbar;         // [0] = hand-off counter, [1] = device-wide abort word; zero at launch
 	unsigned int* err;          // pinned host word: set when a wait gives up
 	const StepParams* step;     // this token's scalars
 	const float* rope_freq;     // (head_dim / 2,)

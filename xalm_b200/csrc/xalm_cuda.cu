@@ -358,18 +358,12 @@ static int launch_matvec(MatvecArgs a, cudaStream_t s, bool pdl) {
 // small kernels
 // ---------------------------------------------------------------------------------------------------------
 // _copy_embedding (infer.cpp:553-602) from the ON-DISK layout of the table (block formats: extension)
-// xt (optional): the same values as {value, tag} words for the token kernel (decode_mega.cu), tagged "embedding" = ar_base + 1
 __global__ void embed_kernel(int type, const uint8_t* __restrict__ table, size_t row_bytes, int dim, const StepParams* step,
-                             float* __restrict__ x, unsigned long long* __restrict__ xt) {
+                             float* __restrict__ x) {
 	pdl_launch_dependents();
 	pdl_wait();
 	const uint8_t* row = table + (size_t) step->token * row_bytes;
-	const unsigned long long tag = (unsigned long long) (step->ar_base + 1u) << 32;
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += gridDim.x * blockDim.x) {
-		const float v = decode_disk_elem(type, row, i);
-		x[i] = v;
-		if (xt) xt[i] = tag | __float_as_uint(v);
-	}
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < dim; i += gridDim.x * blockDim.x) x[i] = decode_disk_elem(type, row, i);
 }
 
 __global__ void dequant_kernel(int type, const uint8_t* __restrict__ src, size_t n, float* __restrict__ dst) {
@@ -762,7 +756,6 @@ struct xalm_cuda_model {
 	size_t dm_smem = 0;
 	int dm_type = 0;
 	int dm_grid = 0;
-	dm_tagged *t_x = nullptr, *t_q = nullptr, *t_xb2 = nullptr, *t_hb = nullptr, *t_kv = nullptr, *t_sink = nullptr, *t_part = nullptr, *t_ml = nullptr;
 	unsigned long long* d_mega_tl = nullptr;
 	size_t mega_tl_words = 0;
 	// batched prefill (prefill.cu)
@@ -1107,35 +1100,13 @@ static int setup_megakernel(xalm_cuda_model* m) {
 	for (int ns = tune("mega_ns_max"); ns >= 2; ns--)
 		if (dm_fixed_smem(xq_cap, ns) + (size_t) ns * slot_bytes <= budget) { NS = ns; break; }
 	if (NS < 2) return XALM_OK;
-	const int kvdiv = G == 8 ? 2 : 1, Gv = G / kvdiv; // 8-head groups run as two virtual kv heads of 4
-	const int n_splits = m->attn_splits;
-	if (n_splits > DM_MAX_SPLITS || c.head_dim > DM_MAX_HD || (m->q_dim_l % 32)) return XALM_OK;
-	if (5 * c.n_layers + 3 >= 1024) return XALM_OK; // tags: ar_base advances by 1024 per token
-	auto talloc = [&](dm_tagged** p, size_t n) -> int {
-		XALM_TRY(m->da.alloc((void**) p, n * sizeof(dm_tagged)));
-		XALM_CUDA_CHECK(cudaMemset(*p, 0, n * sizeof(dm_tagged))); // tag 0 is never produced
-		return XALM_OK;
-	};
-	XALM_TRY(talloc(&m->t_x, c.dim));
-	XALM_TRY(talloc(&m->t_q, m->q_dim_l));
-	XALM_TRY(talloc(&m->t_xb2, m->q_dim_l));
-	XALM_TRY(talloc(&m->t_hb, m->hidden_l));
-	XALM_TRY(talloc(&m->t_kv, m->kv_dim_l));               // K then V row of this token, half2 per word
-	XALM_TRY(talloc(&m->t_sink, (size_t) 2 * m->kv_dim_l / 2)); // KV_SINKS (model.h:10) re-rotated K rows
-	XALM_TRY(talloc(&m->t_part, (size_t) m->n_kv_heads_l * kvdiv * n_splits * Gv * c.head_dim));
-	XALM_TRY(talloc(&m->t_ml, (size_t) m->n_kv_heads_l * kvdiv * n_splits * Gv * 2));
+	if (m->attn_splits > DM_MAX_SPLITS || c.head_dim > DM_MAX_HD || (m->q_dim_l % 32)) return XALM_OK;
 	std::vector<DmPhase> ph;
 	int off = 0;
 	auto mv = [&](const MatvecArgs& a) {
 		DmPhase p = {};
 		p.kind = DM_MATVEC;
 		p.a = a;
-		switch (a.epi) {
-			case EPI_QKV: p.in_t = m->t_x; p.out_t = m->t_q; p.tkv = m->t_kv; p.tsink = m->t_sink; break;
-			case EPI_RESIDUAL: p.in_t = a.x == m->xb2 ? m->t_xb2 : m->t_hb; p.out_t = m->t_x; break;
-			case EPI_GLU: p.in_t = m->t_x; p.out_t = m->t_hb; break;
-			default: p.in_t = m->t_x; p.out_t = nullptr; break; // classifier
-		}
 		const int vrows = a.epi == EPI_GLU ? 2 * a.d : a.d;
 		p.n_tiles = vrows / DM_RC;
 		p.kranges = (a.n / 256 + DM_U - 1) / DM_U;
@@ -1150,7 +1121,6 @@ static int setup_megakernel(xalm_cuda_model* m) {
 		mv(qkv);
 		DmPhase pa = {};
 		pa.kind = DM_ATTN; pa.at = at; pa.G = G; pa.HD = c.head_dim;
-		pa.in_t = m->t_q; pa.out_t = m->t_xb2; pa.tkv = m->t_kv; pa.tsink = m->t_sink; pa.tpart = m->t_part; pa.tml = m->t_ml;
 		pa.tile_off = off;
 		off = (off + at.n_kv_heads * (G == 8 ? 2 : 1) * at.n_splits) % grid;
 		ph.push_back(pa);
@@ -1172,7 +1142,7 @@ static int setup_megakernel(xalm_cuda_model* m) {
 	m->d_phases[0] = m->d_phases[1] = d; // HYDRATE runs the same list minus its last phase
 	XALM_TRY(m->da.alloc((void**) &m->d_gbar, 64));
 	XALM_CUDA_CHECK(cudaMemset(m->d_gbar, 0, 64));
-	m->mega_tl_words = (size_t) ph.size() * (4 + grid);
+	m->mega_tl_words = (size_t) ph.size() * (8 + grid);
 	XALM_TRY(m->da.alloc((void**) &m->d_mega_tl, m->mega_tl_words * sizeof(unsigned long long)));
 	XALM_CUDA_CHECK(cudaMemset(m->d_mega_tl, 0, m->mega_tl_words * sizeof(unsigned long long)));
 	m->dm_args.NS = NS;
@@ -1200,7 +1170,7 @@ static int enqueue_token(xalm_cuda_model* m, int mode, cudaStream_t s, int* n_la
 	int nl = 0;
 	cudaError_t e;
 	e = launch(embed_kernel, dim3(4), dim3(256), s, false, m->embed_type, (const uint8_t*) m->embed_raw, m->embed_row_bytes,
-	                       c.dim, (const StepParams*) m->d_step, m->x, (unsigned long long*) (m->mega ? m->t_x : nullptr));
+	                       c.dim, (const StepParams*) m->d_step, m->x);
 	if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "embed launch failed: %s", cudaGetErrorString(e));
 	nl++;
 	const int G = c.n_heads / c.n_kv_heads;
@@ -1476,21 +1446,6 @@ int xalm_cuda_forward_async(xalm_cuda_model* m, int token, int pos, int mode) {
 	sp.kv_pos = sp.kv_sink + (pos - sp.kv_sink) % (c.max_seq_len - sp.kv_sink);
 	sp.kv_len = pos >= c.max_seq_len ? c.max_seq_len : pos + 1;
 	sp.mode = mode;
-	if (m->mega && m->token_serial >= (1u << 21)) {
-		// tagged hand-off words (decode_mega.cu) compare tags as "at least as new": before the 32-bit tag space wraps, start over from
-		// clean buffers (once every two million tokens)
-		const xalm_config& cc = m->c;
-		const int kvdiv = cc.n_heads / cc.n_kv_heads == 8 ? 2 : 1, Gv = cc.n_heads / cc.n_kv_heads / kvdiv;
-		XALM_CUDA_CHECK(cudaMemsetAsync(m->t_x, 0, (size_t) cc.dim * sizeof(dm_tagged), s));
-		XALM_CUDA_CHECK(cudaMemsetAsync(m->t_q, 0, (size_t) m->q_dim_l * sizeof(dm_tagged), s));
-		XALM_CUDA_CHECK(cudaMemsetAsync(m->t_xb2, 0, (size_t) m->q_dim_l * sizeof(dm_tagged), s));
-		XALM_CUDA_CHECK(cudaMemsetAsync(m->t_hb, 0, (size_t) m->hidden_l * sizeof(dm_tagged), s));
-		XALM_CUDA_CHECK(cudaMemsetAsync(m->t_kv, 0, (size_t) m->kv_dim_l * sizeof(dm_tagged), s));
-		XALM_CUDA_CHECK(cudaMemsetAsync(m->t_sink, 0, (size_t) m->kv_dim_l * sizeof(dm_tagged), s));
-		XALM_CUDA_CHECK(cudaMemsetAsync(m->t_part, 0, (size_t) m->n_kv_heads_l * kvdiv * m->attn_splits * Gv * cc.head_dim * sizeof(dm_tagged), s));
-		XALM_CUDA_CHECK(cudaMemsetAsync(m->t_ml, 0, (size_t) m->n_kv_heads_l * kvdiv * m->attn_splits * Gv * 2 * sizeof(dm_tagged), s));
-		m->token_serial = 0;
-	}
 	sp.ar_base = m->token_serial * 1024u; // 2 x n_layers <= 1024 exchanges per token; wraps consistently on every rank
 	m->token_serial++;
 	XALM_CUDA_CHECK(cudaMemcpyAsync(m->d_step, &sp, sizeof sp, cudaMemcpyHostToDevice, s));
