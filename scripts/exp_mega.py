@@ -44,7 +44,11 @@ def perf(shape, wtname, layers=None):
     K = 64
     pos = bench.positions_for(K, 4096)
     ref_tok = None
-    for mega in (1, 0):
+    cfgs = [dict(kv.split("=") for kv in c.split(",")) for c in os.environ.get("CONFIGS", "mega=1;mega=0").split(";")]
+    for cfgd in cfgs:
+        for k, v in cfgd.items():
+            capi.tune(k, int(v))
+        mega = int(cfgd.get("mega", 0))
         capi.tune("mega", mega)
         capi.tune("mega_timeline", 1 if mega else 0)
         model = Model.from_tensors(cfg, tensors).cuda(device=0, stream=st.cuda_stream)
@@ -65,7 +69,7 @@ def perf(shape, wtname, layers=None):
             res.append(f"{label}: {ms/K:.3f} ms/tok {K/(ms/1e3):.0f} tok/s {byts*K/(ms/1e3)/1e9:.0f} GB/s")
         model.sync()
         lg = model.read_state(capi.S_LOGITS, cfg["vocab_size"])
-        print(f"{shape} {wtname} mega={mega}: " + " | ".join(res) + f" launches/token {model.last_launch_count()} argmax {int(np.argmax(lg))}", flush=True)
+        print(f"{shape} {wtname} {cfgd}: " + " | ".join(res) + f" launches/token {model.last_launch_count()} argmax {int(np.argmax(lg))}", flush=True)
         if ref_tok is None:
             ref_lg = lg
         else:

@@ -153,7 +153,7 @@ __device__ __forceinline__ void dm_load_block(const float* x, float (&v)[32]) {
 // reduction.  Longer rows park the raw values in `stash` (the tail of the activation area) and take the norm weights late.
 // Out of line on purpose: its 64 registers of block + weights must not weigh on the allocation of the tile loop.  The hand-off
 // wait sits inside so that the norm weights travel while the counter is polled.
-__device__ __forceinline__ void dm_stage_norm(const MatvecArgs& a, uint8_t* xq_base, float* s_red, float* stash, unsigned int* ctr, unsigned int expected,
+__device__ __noinline__ void dm_stage_norm(const MatvecArgs& a, uint8_t* xq_base, float* s_red, float* stash, unsigned int* ctr, unsigned int expected,
                                            bool do_wait, const DmAbort ab, unsigned long long* tls) {
 	const int n = a.n, nb = n / 32;
 	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -200,7 +200,7 @@ __device__ __forceinline__ void dm_stage_norm(const MatvecArgs& a, uint8_t* xq_b
 		xq_store_block(v, blk, t);
 	}
 }
-__device__ __forceinline__ void dm_stage_plain(const MatvecArgs& a, uint8_t* xq_base) {
+__device__ __noinline__ void dm_stage_plain(const MatvecArgs& a, uint8_t* xq_base) {
 	const XqView v = xq_view(xq_base, a.n);
 	const int nb = a.n / 32;
 	for (int blk = threadIdx.x; blk < nb; blk += DM_CW * 32) {
@@ -216,7 +216,7 @@ __device__ __forceinline__ void dm_stage_plain(const MatvecArgs& a, uint8_t* xq_
 // second pass re-reads the K/V slice from L2).  The first K/V batch is requested BEFORE the hand-off wait; rows written during
 // this token (kv_pos; the re-rotated sinks) are fetched again after it.
 template <int HD, int G, int KVDIV>
-__device__ __forceinline__ unsigned int dm_attention(const DmPhase& P, const StepParams& st, float* scratch, int first, int stride, const DmAbort ab,
+__device__ __noinline__ unsigned int dm_attention(const DmPhase& P, const StepParams& st, float* scratch, int first, int stride, const DmAbort ab,
                                                      unsigned int* ctr, unsigned int expected, bool wait_first, unsigned long long* tls) {
 	constexpr int NW = DM_CW;
 	constexpr int LPR = HD / 8, RPW = 32 / LPR, TB = 4, NGRP = NW * RPW;
@@ -581,10 +581,12 @@ __global__ void __launch_bounds__(DM_THREADS, 1) decode_token_kernel(const DmArg
 	__shared__ float2 s_rope[DM_MAX_HD / 2]; // {cos, sin}(pos * freq[j]): the QKV epilogue's rotation (infer.cpp:305-322) without a libm call per pair
 	__shared__ int s_abort;
 	__shared__ DmTileCtx s_ctx;
+	__shared__ int s_quiet; // consumers are between phases (hand-off, staging, attention): the producer holds its copies back (mk.quiet)
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	if (threadIdx.x == 0) {
 		s_abort = 0;
+		s_quiet = 0;
 		s_ctx = {xq_base, ring, part, full, empty, &s_abort, &s_step, s_rope, mk.slot_bytes, NS};
 		for (int s = 0; s < NS; s++) {
 			mbar_init(&full[s], 1);
@@ -623,6 +625,12 @@ __global__ void __launch_bounds__(DM_THREADS, 1) decode_token_kernel(const DmArg
 					const int row0 = tile * RC;
 					for (int kr = 0; kr < kranges; kr++) {
 						if (!dm_mbar_wait(&empty[slot], phase ^ 1, &s_abort)) return;
+						if (mk.quiet) { // loads from L2 take ~2 us behind a saturated copy stream: leave the memory system to the consumers' hand-off
+							while (*reinterpret_cast<volatile int*>(&s_quiet)) {
+								if (*reinterpret_cast<volatile int*>(&s_abort)) return;
+								__nanosleep(64);
+							}
+						}
 						const int u0 = kr * U;
 						const int un = min(U, nu - u0);
 						const uint32_t bytes = (uint32_t) un * UB;
@@ -694,6 +702,7 @@ __global__ void __launch_bounds__(DM_THREADS, 1) decode_token_kernel(const DmArg
 				if (norm) dm_stage_norm(a, xq_base, s_red, reinterpret_cast<float*>(xq_base + mk.xq_cap) - n, mk.gbar, expected, ph > 0, ab, tl ? tl + 8 * ph : nullptr); // host: xq_cap >= xq_bytes(n) + 4 n
 				else dm_stage_plain(a, xq_base);
 				dm_bar();
+				if (threadIdx.x == 0) *reinterpret_cast<volatile int*>(&s_quiet) = 0;
 				if (tl) tl[8 * ph + 2] = gtime();
 
 				cursor = dm_tiles<TYPE>(P, s_ctx, first, cursor, tl ? tl + 8 * ph : nullptr);
@@ -701,6 +710,7 @@ __global__ void __launch_bounds__(DM_THREADS, 1) decode_token_kernel(const DmArg
 			if (tl) tl[8 * ph + 3] = gtime();
 		}
 		if (has_next) reinterpret_cast<uint32_t*>(&s_ph[(ph + 1) & 1])[threadIdx.x] = next_word;
+		if (threadIdx.x == 0) *reinterpret_cast<volatile int*>(&s_quiet) = 1;
 		dm_signal(mk.gbar); // (its barrier: every warp is done with this phase's staged activations, partial sums and descriptor)
 		expected += (unsigned int) G;
 	}

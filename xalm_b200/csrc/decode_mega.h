@@ -30,6 +30,7 @@ struct DmArgs {
 	const StepParams* step;     // this token's scalars
 	const float* rope_freq;     // (head_dim / 2,)
 	int head_dim;
+	int quiet;                  // 1: the producer holds its copies back while the consumers are between phases
 	unsigned long long* tl;     // optional timeline: tl_phases x 4 stamps of CTA 0, then tl_phases x grid phase-entry stamps (or nullptr)
 	int tl_phases;              // phases the timeline buffer was sized for
 };

@@ -1,0 +1,315 @@
+// matvec_idp.cuh — the TMA decode matvec (matvec_tma.cuh) for the integer weight formats, on the integer-dot core (idp.cuh).
+//
+// Same skeleton as matvec_tma_kernel — persistent CTAs, a producer warp streaming rows into an mbarrier ring with
+// cp.async.bulk, 8 consumer warps, rmsnorm prologue, QKV / GLU / residual / store epilogues, PDL, the fused tensor-parallel
+// exchange — but the consumers work in integers: the activations are staged ONCE per CTA as block floating point (three int8
+// limbs per element + one power-of-two scale per 32), and a 32-weight block costs 24 dp4a plus ~8 finishing instructions
+// instead of 64-136 PRMT / FADD2 / FFMA2.  Measured on the float core (profiles/r1_matvec_tma_q8_0_w13.md): q8_0 issue /
+// latency-bound at 75 % of HBM peak (3.9 issue slots per weight with its per-tile reductions), q4_0..q5_1 ALU-bound at 26-29 %.
+//
+// Mapping: a tile is 8 rows, a ring stage 8 rows x 16 units (4096 elements).  Warp (kw, rw) = K-slice kw of 4 (32 blocks of 32
+// elements: one block per lane) x row group rw of 2 (4 rows).  Per stage a lane loads its activation block once (7 shared
+// loads) and walks its 4 rows.  Lane sums are reduced with a 6-shuffle transposed butterfly; K-slices are combined through
+// shared memory in a fixed order (bit-reproducible run to run); a rotating warp runs the epilogue.
+#pragma once
+#include "idp.cuh"
+#include "matvec_tma.cuh"
+
+namespace xalm {
+
+constexpr int IDP_KW = 4, IDP_RW = 2, IDP_R = 4, IDP_RC = IDP_RW * IDP_R, IDP_U = 16;
+
+__host__ __device__ inline size_t idp_smem_bytes(int type, int n, int NS) {
+	size_t s = (xq_bytes(n) + 127) / 128 * 128;
+	s += (size_t) NS * IDP_RC * IDP_U * unit_bytes(type);
+	s += 2 * IDP_KW * IDP_RC * sizeof(float);   // partials, double-buffered
+	s += 2 * (size_t) NS * sizeof(uint64_t);    // full / empty barriers
+	s += 16 * sizeof(float);                    // reduction scratch
+	return s + 128;
+}
+
+struct IdpArgs {
+	MatvecArgs a;   // a.w.p0 = unit-interleaved rows, a.w.s0 = row stride in bytes
+	int NS;         // ring stages
+	int n_tiles;    // virtual rows / 8
+};
+
+template <int TYPE, bool NORM>
+// <= 96 registers: the register file is per scheduler (16 K each), two CTAs of 9 warps need 5 warps on one of them: 16384 / 5 / 32 = 102
+__global__ void __maxnreg__(96) matvec_idp_kernel(const IdpArgs ta) {
+	using F = IdpFmt<TYPE>;
+	constexpr int KW = IDP_KW, R = IDP_R, RC = IDP_RC, U = IDP_U, UB = F::UB;
+	constexpr int ROW_STAGE = U * UB;
+	constexpr int SLOT = RC * ROW_STAGE;
+	const MatvecArgs& a = ta.a;
+	const int NS = ta.NS;
+	const int n = a.n, nu = n / 256, nb_row = n / 32;
+	const int kranges = (nu + U - 1) / U;
+
+	extern __shared__ __align__(128) uint8_t smem[];
+	uint8_t* xq_base = smem;
+	uint8_t* ring = smem + (xq_bytes(n) + 127) / 128 * 128;
+	float* part = reinterpret_cast<float*>(ring + (size_t) NS * SLOT);
+	float* s_red = part + 2 * KW * RC;
+	uint64_t* full = reinterpret_cast<uint64_t*>(s_red + 16);
+	uint64_t* empty = full + NS;
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	if (threadIdx.x == 0) {
+		for (int s = 0; s < NS; s++) {
+			mbar_init(&full[s], 1);
+			mbar_init(&empty[s], TMA_NW);
+		}
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	__syncthreads();
+	pdl_launch_dependents();
+	int tl = -1;
+	if (blockIdx.x == 0 && threadIdx.x == 0) tl = tl_begin(100 + a.epi);
+
+	const int my_tiles = ((int) blockIdx.x < ta.n_tiles) ? (ta.n_tiles - 1 - (int) blockIdx.x) / (int) gridDim.x + 1 : 0;
+
+	if (warp == TMA_NW) {
+		// ===================== producer: weights only — runs ahead of griddepcontrol.wait =====================
+		if (lane == 0) {
+			int slot = 0, phase = 0;
+			for (int tt = 0; tt < my_tiles; tt++) {
+				const int row0 = ((int) blockIdx.x + tt * (int) gridDim.x) * RC;
+				for (int kr = 0; kr < kranges; kr++) {
+					mbar_wait(&empty[slot], phase ^ 1);
+					const int u0 = kr * U;
+					const int un = min(U, nu - u0);
+					const uint32_t bytes = (uint32_t) un * UB;
+					mbar_expect_tx(&full[slot], bytes * RC);
+					uint8_t* dst = ring + (size_t) slot * SLOT;
+					if (un == nu && nu == U && a.w.s0 == (size_t) ROW_STAGE) {
+						// the stage spans whole rows and a tile's rows are neighbours in memory: ONE copy per run of rows instead of
+						// one per row (the copy engine is bound by the NUMBER of bulk copies when they are a few KB each: q4_0 rows of
+						// 2304 bytes streamed no faster than q8_0 rows of 4352, profiles/r2_decode_timeline.md)
+						if (a.epi == EPI_GLU) { // rows [0, RC/2) are W1[o0..], rows [RC/2, RC) are W3[o0..]
+							const int o0 = row0 / 2;
+							bulk_g2s(dst, a.w.p0 + (size_t) o0 * a.w.s0, bytes * (RC / 2), &full[slot]);
+							bulk_g2s(dst + (size_t) (RC / 2) * ROW_STAGE, a.w.p0 + (size_t) (a.glu_off + o0) * a.w.s0, bytes * (RC / 2), &full[slot]);
+						} else {
+							bulk_g2s(dst, a.w.p0 + (size_t) row0 * a.w.s0, bytes * RC, &full[slot]);
+						}
+					} else {
+#pragma unroll
+						for (int r = 0; r < RC; r++) {
+							const int pr = phys_row(a, row0, r, RC);
+							bulk_g2s(dst + (size_t) r * ROW_STAGE, a.w.p0 + (size_t) pr * a.w.s0 + (size_t) u0 * UB, bytes, &full[slot]);
+						}
+					}
+					if (++slot == NS) { slot = 0; phase ^= 1; }
+				}
+			}
+			l2_prefetch_slice(a.pf_ptr, a.pf_bytes, (int) blockIdx.x, (int) gridDim.x);
+			if (a.pf_kv) {
+				const unsigned long long kvb = (unsigned long long) a.step->kv_len * a.kv_dim * sizeof(__half);
+				l2_prefetch_slice(reinterpret_cast<const uint8_t*>(a.k_cache), kvb, (int) blockIdx.x, (int) gridDim.x);
+				l2_prefetch_slice(reinterpret_cast<const uint8_t*>(a.v_cache), kvb, (int) blockIdx.x, (int) gridDim.x);
+			}
+		}
+		return;
+	}
+
+	// ===================== consumers =====================
+	// Staging: thread t owns 32-element block t (+256, ...).  The rmsnorm weights of that block do not depend on the previous
+	// kernel: request them before the dependency wait (host: NORM only with n <= 8192, one block per thread).
+	const int tid = threadIdx.x;
+	uint4 gw[NORM ? 4 : 1]; // BF16 weights travel packed (16 registers); F32 ones are pulled into L2 now and read after the reduction
+	if (NORM && tid < nb_row) {
+		if (a.norm_type == XALM_F32) {
+			asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const float*>(a.norm_w) + tid * 32));
+		} else {
+#pragma unroll
+			for (int c = 0; c < 4; c++) gw[c] = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.norm_w) + tid * 32 + 8 * c);
+		}
+	}
+	pdl_wait(); // activations / KV ring of earlier kernels are visible from here on
+	tl_mark(tl, 2);
+	if (a.epi == EPI_QKV && blockIdx.x == 0 && a.step->kv_sink > 0) {
+		const int pairs = a.kv_dim / 2;
+		for (int i = threadIdx.x; i < a.step->kv_sink * pairs; i += TMA_NW * 32) {
+			const int r = i / pairs, p = i % pairs;
+			__half2* kp = reinterpret_cast<__half2*>(a.k_cache + (size_t) r * a.kv_dim) + p;
+			float2 v = __half22float2(*kp);
+			rope_pair(v.x, v.y, (2 * p) % a.head_dim, 1, a.rope_freq);
+			*kp = __floats2half2_rn(v.x, v.y);
+		}
+	}
+	// ---- tensor-parallel receive (LL style), as in matvec_tma_kernel: the first CTAs each reduce a slice of the stream and publish
+	//      it locally as {value, tag} words ----
+	if (NORM && a.n_recv) {
+		const int n_red = min((int) gridDim.x, 8);
+		if ((int) blockIdx.x < n_red) {
+			const unsigned int seq = a.step->ar_base + (unsigned int) a.recv_idx + 1u;
+			const int chunk = ((n / 4 + n_red - 1) / n_red) * 4;
+			const int i0 = (int) blockIdx.x * chunk, i1 = min(n, i0 + chunk);
+			for (int i = i0 + (int) threadIdx.x * 4; i < i1; i += TMA_NW * 32 * 4) {
+				float4 v = ld_act4(a.x + i);
+				float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+				for (int p = 0; p < a.n_recv; p++) {
+					const uint2* src = a.recv + (size_t) p * n + i; // four {value, tag} words; poll until all carry this exchange's tag
+					uint4 w0, w1;
+					unsigned int spins = 0;
+					do {
+						asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w0.x), "=r"(w0.y), "=r"(w0.z), "=r"(w0.w) : "l"(src));
+						asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w1.x), "=r"(w1.y), "=r"(w1.z), "=r"(w1.w) : "l"(src + 2));
+						if (++spins > XALM_SPIN_LIMIT) { if (a.err_flag) *a.err_flag = 1u; break; } // a peer died: report, do not hang the GPU
+					} while (w0.y != seq || w0.w != seq || w1.y != seq || w1.w != seq);
+					sum.x += __uint_as_float(w0.x); sum.y += __uint_as_float(w0.z); sum.z += __uint_as_float(w1.x); sum.w += __uint_as_float(w1.z);
+				}
+				v.x += sum.x; v.y += sum.y; v.z += sum.z; v.w += sum.w;
+				*reinterpret_cast<float4*>(a.x_out + i) = v;
+				*reinterpret_cast<uint4*>(a.xl + i) = make_uint4(__float_as_uint(v.x), seq, __float_as_uint(v.y), seq);
+				*reinterpret_cast<uint4*>(a.xl + i + 2) = make_uint4(__float_as_uint(v.z), seq, __float_as_uint(v.w), seq);
+			}
+		}
+	}
+	// ---- stage activations: xq = quantise(NORM ? x * scale * g : x) ----
+	const XqView xv = xq_view(xq_base, n);
+	{
+		auto load_block = [&](int blk, float (&v)[32]) {
+			if (NORM && a.n_recv) { // the summed stream, published by the reducing CTAs as {value, tag} words: poll this exchange's tag
+				const unsigned int seq = a.step->ar_base + (unsigned int) a.recv_idx + 1u;
+#pragma unroll
+				for (int c = 0; c < 8; c++) {
+					const uint2* src = a.xl + blk * 32 + 4 * c;
+					uint4 w0, w1;
+					unsigned int spins = 0;
+					do {
+						asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w0.x), "=r"(w0.y), "=r"(w0.z), "=r"(w0.w) : "l"(src));
+						asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w1.x), "=r"(w1.y), "=r"(w1.z), "=r"(w1.w) : "l"(src + 2));
+						if (++spins > XALM_SPIN_LIMIT) { if (a.err_flag) *a.err_flag = 1u; break; }
+					} while (w0.y != seq || w0.w != seq || w1.y != seq || w1.w != seq);
+					v[4 * c] = __uint_as_float(w0.x); v[4 * c + 1] = __uint_as_float(w0.z); v[4 * c + 2] = __uint_as_float(w1.x); v[4 * c + 3] = __uint_as_float(w1.z);
+				}
+			} else {
+#pragma unroll
+				for (int c = 0; c < 8; c++) {
+					const float4 q = ld_act4(a.x + blk * 32 + 4 * c);
+					v[4 * c] = q.x; v[4 * c + 1] = q.y; v[4 * c + 2] = q.z; v[4 * c + 3] = q.w;
+				}
+			}
+		};
+		if (NORM) {
+			float xr[32];
+			float ss = 0.f;
+			if (tid < nb_row) {
+				load_block(tid, xr);
+#pragma unroll
+				for (int e = 0; e < 32; e++) ss += xr[e] * xr[e];
+			}
+			ss = warp_sum(ss);
+			if (lane == 0) s_red[warp] = ss;
+			consumer_bar_sync();
+			float tot = 0.f;
+#pragma unroll
+			for (int i = 0; i < TMA_NW; i++) tot += s_red[i];
+			const float scale = 1.0f / sqrtf(tot / (float) n + a.norm_eps);
+			if (tid < nb_row) {
+#pragma unroll
+				for (int e = 0; e < 32; e++) {
+					float g;
+					if (a.norm_type == XALM_F32) {
+						g = reinterpret_cast<const float*>(a.norm_w)[tid * 32 + e];
+					} else {
+						const uint4 q = gw[e >> 3];
+						const int h = (e & 7) >> 1;
+						const uint32_t u = h == 0 ? q.x : h == 1 ? q.y : h == 2 ? q.z : q.w;
+						g = __uint_as_float((e & 1) ? (u & 0xFFFF0000u) : (u << 16));
+					}
+					xr[e] = xr[e] * scale * g; // infer.cpp:233-235
+				}
+				xq_store_block(xv, tid, xr);
+			}
+		} else {
+			for (int blk = tid; blk < nb_row; blk += TMA_NW * 32) {
+				float xr[32];
+				load_block(blk, xr);
+				xq_store_block(xv, blk, xr);
+			}
+		}
+		consumer_bar_sync();
+	}
+
+	const int kw = warp % KW, rw = warp / KW;
+	const int hA = (lane >> 2) & 1;
+	int slot = 0, phase = 0;
+	for (int tt = 0; tt < my_tiles; tt++) {
+		const int row0 = ((int) blockIdx.x + tt * (int) gridDim.x) * RC;
+		const bool reducer = warp == (tt % TMA_NW);
+		float xold = 0.f; // residual: the reducer warp fetches the old activation now, so its epilogue does not sit on an L2 round trip
+		if (a.epi == EPI_RESIDUAL && reducer && lane < RC && row0 + lane < a.d) xold = a.out[row0 + lane];
+		float y[R];
+#pragma unroll
+		for (int r = 0; r < R; r++) y[r] = 0.f;
+		for (int kr = 0; kr < kranges; kr++) {
+			const int u0 = kr * U;
+			const int nb = 8 * min(U, nu - u0); // blocks per row in this stage
+			const int b = kw * 32 + lane;
+			mbar_wait(&full[slot], phase);
+			if (b < nb) {
+				XqBlock xb;
+				xq_load(xv, u0 * 8 + b, hA, xb);
+				const uint8_t* unit = ring + (size_t) slot * SLOT + (size_t) (rw * R) * ROW_STAGE + (size_t) (b >> 3) * UB;
+#pragma unroll
+				for (int r = 0; r < R; r++) F::block(unit + (size_t) r * ROW_STAGE, b & 7, hA, xb, y[r]);
+			}
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&empty[slot]);
+			if (++slot == NS) { slot = 0; phase ^= 1; }
+		}
+		// ---- lanes -> one sum per row (transposed butterfly: 6 shuffles for 4 rows), K-slices -> shared memory (fixed order) ----
+		{
+			const bool b4 = lane & 16, b3 = lane & 8;
+			float k0 = b4 ? y[2] : y[0], k1 = b4 ? y[3] : y[1];
+			const float s0 = b4 ? y[0] : y[2], s1 = b4 ? y[1] : y[3];
+			k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+			k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+			float k = b3 ? k1 : k0;
+			const float s = b3 ? k0 : k1;
+			k += __shfl_xor_sync(0xffffffffu, s, 8);
+			k += __shfl_xor_sync(0xffffffffu, k, 4);
+			k += __shfl_xor_sync(0xffffffffu, k, 2);
+			k += __shfl_xor_sync(0xffffffffu, k, 1);
+			if ((lane & 7) == 0) part[(tt & 1) * (KW * RC) + kw * RC + rw * R + (b4 ? 2 : 0) + (b3 ? 1 : 0)] = k;
+		}
+		consumer_bar_sync();
+		if (reducer) { // rotating reducer: lane i owns row i of the tile
+			const float* pt = part + (tt & 1) * (KW * RC);
+			float yv = 0.f;
+			if (lane < RC) {
+#pragma unroll
+				for (int k = 0; k < KW; k++) yv += pt[k * RC + lane];
+			}
+			const float ynext = __shfl_down_sync(0xffffffffu, yv, 1);
+			if (a.epi == EPI_RESIDUAL) {
+				if (lane < RC && row0 + lane < a.d) a.out[row0 + lane] = xold + yv;
+			} else if (a.epi == EPI_STORE && a.n_push) { // tensor parallel: this rank's partial rows go to every rank (NVLink stores)
+				if (lane < RC && (lane & 1) == 0 && row0 + lane < a.d) {
+					const unsigned int seq = a.step->ar_base + (unsigned int) a.push_idx + 1u;
+					const uint4 w = make_uint4(__float_as_uint(yv), seq, __float_as_uint(ynext), seq);
+					for (int p = 0; p < a.n_push; p++) *reinterpret_cast<uint4*>(a.push_dst[p] + row0 + lane) = w;
+				}
+			} else if (lane < RC && (lane & 1) == 0 && a.epi != EPI_GLU) { // GLU below (partner rows RC/2 apart)
+				const float y2[2] = {yv, ynext};
+				epilogue<2>(a, row0 + lane, y2);
+			}
+			if (a.epi == EPI_GLU) {
+				const float ypart = __shfl_down_sync(0xffffffffu, yv, RC / 2); // W3 value for the W1 row in this lane
+				if (lane < RC / 2) {
+					const int o = row0 / 2 + lane;
+					if (o < a.d) {
+						const float g = a.act == XALM_SILU ? act_silu(yv) : act_gelu(yv);
+						a.out[o] = g * ypart;
+					}
+				}
+			}
+		}
+	}
+	tl_mark(tl, 3);
+}
+
+} // namespace xalm

@@ -27,6 +27,7 @@
 #include "attention.cuh"
 #include "matvec.cuh"
 #include "matvec_tma.cuh"
+#include "matvec_idp.cuh"
 #include "decode_mega.h"
 #include "prefill.h"
 
@@ -54,13 +55,16 @@ static std::map<std::string, int>& tuning() {
 	    {"attn_splits", 0},  // 0 = auto (~1 CTA per SM, at most 32 splits per kv head)
 	    {"attn_min_split", 128},
 	    {"mv_cfg_rows", 0},  // 0 = auto, 1 = force config A (R4 KS1 NW4), 2 = force config B (R2 KS4 NW8)
-	    {"mega", 1},         // one persistent kernel per token (decode_mega.cu) when the model allows: single GPU, integer weight formats
+	    {"mega", 0},         // EXPERIMENTAL, measured slower than the kernel-per-op path (profiles/r2_token_kernel.md): one persistent kernel per
+	                         // token (decode_mega.cu) when the model allows — single GPU, integer weight formats
 	    {"mega_smem_kb", 170}, // shared memory per CTA the token kernel may take: the ring gets what the staged activations leave (3 stages on a
 	                           // 7B model: deeper rings measured no faster), the rest of the 228 KB stays L1
 	    {"mega_ns_max", 16},
+	    {"mega_quiet", 1},   // the token kernel's producer pauses while the consumers hand over between phases
 	    {"mega_coop", 1},    // cooperative launch of the token kernel
 	    {"mega_timeline", 0}, // record per-phase %globaltimer stamps (xalm_cuda_mega_timeline)
 	    {"tma", 1},          // stream weights with cp.async.bulk into a shared-memory ring (matvec_tma.cuh)
+	    {"idp", 1},          // integer weight formats: integer-dot consumers (matvec_idp.cuh) instead of the float ones
 	    {"tma_smem_kb", 100}, // shared-memory budget per CTA for the TMA kernel (two kernels co-reside under PDL)
 	    {"tma_rc_small", 8}, // rows per tile when the matrix has few rows (Wo, W2)
 	    {"tma_xstage_max_kb", 32}, // rows longer than this (in fp32 bytes) are not staged in smem when there is no norm
@@ -145,33 +149,50 @@ static cudaError_t launch_matvec_typed(const MatvecArgs& a, const MvCfg& c, bool
 // ---------------------------------------------------------------------------------------------------------
 // TMA matvec dispatch (matvec_tma.cuh)
 // ---------------------------------------------------------------------------------------------------------
-static int g_num_sms = 0;
+static int current_device() {
+	int dev = 0;
+	cudaGetDevice(&dev);
+	return dev;
+}
+// SM count of the CURRENT device (function attributes, occupancy and SM counts are per device: a handle may live on any GPU)
 static int num_sms() {
-	if (!g_num_sms) {
-		int dev = 0;
-		g_num_sms = 148;
-		if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+	static std::map<int, int> cache;
+	const int dev = current_device();
+	auto it = cache.find(dev);
+	if (it == cache.end()) {
+		int n = 148;
+		cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+		it = cache.emplace(dev, n).first;
 	}
-	return g_num_sms;
+	return it->second;
+}
+// opt a kernel into > 48 KB of dynamic shared memory, once per (kernel, device)
+template <typename K>
+static cudaError_t ensure_smem_attr(K kern, int bytes) {
+	static std::map<std::pair<const void*, int>, bool> done; // (kernel, device): one instantiation serves every kernel of a signature
+	const std::pair<const void*, int> key(reinterpret_cast<const void*>(kern), current_device());
+	if (done.count(key)) return cudaSuccess;
+	cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+	if (e == cudaSuccess) done[key] = true;
+	return e;
 }
 
 template <int TYPE, int RC, int KW, bool NORM>
 static cudaError_t launch_tma_inst(const TmaArgs& ta, int max_ctas_per_sm, size_t smem, cudaStream_t s, bool pdl) {
-	static bool attr_set = false;
-	static std::map<size_t, int> occ_cache;
+	static std::map<std::pair<int, size_t>, int> occ_cache; // (device, smem) -> resident CTAs per SM
 	auto kern = matvec_tma_kernel<TYPE, RC, KW, NORM>;
-	if (!attr_set) {
-		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+	{
+		cudaError_t e = ensure_smem_attr(kern, 200 * 1024);
 		if (e != cudaSuccess) return e;
-		attr_set = true;
 	}
 	// persistent grid: exactly as many CTAs as can be resident at once (a second wave would serialise behind the first)
-	auto it = occ_cache.find(smem);
+	const std::pair<int, size_t> key(current_device(), smem);
+	auto it = occ_cache.find(key);
 	if (it == occ_cache.end()) {
 		int occ = 1;
 		cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (TMA_NW + 1) * 32, smem);
 		if (e != cudaSuccess) return e;
-		it = occ_cache.emplace(smem, occ < 1 ? 1 : occ).first;
+		it = occ_cache.emplace(key, occ < 1 ? 1 : occ).first;
 	}
 	int per_sm = it->second < max_ctas_per_sm ? it->second : max_ctas_per_sm;
 	int grid = num_sms() * per_sm;
@@ -296,6 +317,73 @@ static int launch_matvec_tma(const MatvecArgs& a, cudaStream_t s, bool pdl) {
 	return XALM_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// integer-dot matvec dispatch (matvec_idp.cuh): the integer weight formats in unit layout
+// ---------------------------------------------------------------------------------------------------------
+template <int TYPE, bool NORM>
+static cudaError_t launch_idp_inst(const IdpArgs& ta, size_t smem, int max_ctas_per_sm, cudaStream_t s, bool pdl) {
+	static std::map<std::pair<int, size_t>, int> occ_cache;
+	auto kern = matvec_idp_kernel<TYPE, NORM>;
+	cudaError_t e = ensure_smem_attr(kern, 220 * 1024);
+	if (e != cudaSuccess) return e;
+	const std::pair<int, size_t> key(current_device(), smem);
+	auto it = occ_cache.find(key);
+	if (it == occ_cache.end()) {
+		int occ = 1;
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (TMA_NW + 1) * 32, smem);
+		if (e != cudaSuccess) return e;
+		it = occ_cache.emplace(key, occ < 1 ? 1 : occ).first;
+	}
+	const int per_sm = it->second < max_ctas_per_sm ? it->second : max_ctas_per_sm;
+	int grid = num_sms() * per_sm; // persistent: exactly the CTAs that can be resident at once
+	if (grid > ta.n_tiles) grid = ta.n_tiles;
+	return launch_smem(kern, dim3(grid), dim3((TMA_NW + 1) * 32), smem, s, pdl, ta);
+}
+template <int TYPE>
+static cudaError_t launch_idp_typed(const IdpArgs& ta, bool norm, size_t smem, int per_sm, cudaStream_t s, bool pdl) {
+	return norm ? launch_idp_inst<TYPE, true>(ta, smem, per_sm, s, pdl) : launch_idp_inst<TYPE, false>(ta, smem, per_sm, s, pdl);
+}
+// returns -1 when the matrix cannot go down this path (the caller falls back to the float kernels)
+static int launch_matvec_idp(const MatvecArgs& a, cudaStream_t s, bool pdl) {
+	const int t = a.w.type;
+	if (!tune("idp") || !tune("tma") || !idp_supported(t)) return -1;
+	TypeInfo ti;
+	type_info(t, &ti);
+	if (ti.block > 1 ? !a.w.layout_units : a.w.s0 != (size_t) a.n) return -1;
+	const int vrows = a.epi == EPI_GLU ? 2 * a.d : a.d;
+	if (a.n % 256 || vrows % IDP_RC) return -1;
+	const bool norm = a.norm_w != nullptr;
+	if (norm && a.n > 8192) return -1; // the norm-fused staging keeps one 32-element block per thread in registers
+	// two CTAs per SM when the staged activations leave room for >= 2 ring stages each (kernels overlap under PDL), else one deep ring
+	const size_t budget2 = (size_t) tune("tma_smem_kb") * 1024;
+	int NS = 0, per_sm = 2;
+	for (int ns = tune("tma_ns_max"); ns >= 2; ns--)
+		if (idp_smem_bytes(t, a.n, ns) <= budget2) { NS = ns; break; }
+	if (!NS) {
+		per_sm = 1;
+		for (int ns = 5; ns >= 2; ns--)
+			if (idp_smem_bytes(t, a.n, ns) <= 216 * 1024) { NS = ns; break; }
+	}
+	if (!NS) return -1;
+	IdpArgs ta;
+	ta.a = a;
+	ta.NS = NS;
+	ta.n_tiles = vrows / IDP_RC;
+	const size_t smem = idp_smem_bytes(t, a.n, NS);
+	cudaError_t e;
+	switch (t) {
+		case XALM_Q8_0: e = launch_idp_typed<XALM_Q8_0>(ta, norm, smem, per_sm, s, pdl); break;
+		case XALM_Q8: e = launch_idp_typed<XALM_Q8>(ta, norm, smem, per_sm, s, pdl); break;
+		case XALM_Q4_0: e = launch_idp_typed<XALM_Q4_0>(ta, norm, smem, per_sm, s, pdl); break;
+		case XALM_Q4_1: e = launch_idp_typed<XALM_Q4_1>(ta, norm, smem, per_sm, s, pdl); break;
+		case XALM_Q5_0: e = launch_idp_typed<XALM_Q5_0>(ta, norm, smem, per_sm, s, pdl); break;
+		case XALM_Q5_1: e = launch_idp_typed<XALM_Q5_1>(ta, norm, smem, per_sm, s, pdl); break;
+		default: return -1;
+	}
+	if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "matvec (idp) launch failed: %s", cudaGetErrorString(e));
+	return XALM_OK;
+}
+
 static int launch_matvec(MatvecArgs a, cudaStream_t s, bool pdl) {
 	const bool norm = a.norm_w != nullptr;
 	if (norm && a.norm_type != XALM_F32 && a.norm_type != XALM_BF16)
@@ -305,6 +393,10 @@ static int launch_matvec(MatvecArgs a, cudaStream_t s, bool pdl) {
 	const int vrows = a.epi == EPI_GLU ? 2 * a.d : a.d;
 	int t = a.w.type;
 	cudaError_t e;
+	{
+		const int rc = launch_matvec_idp(a, s, pdl);
+		if (rc >= 0) return rc;
+	}
 	if (a.w.layout_units) {
 		const int rc = launch_matvec_tma(a, s, pdl);
 		if (rc >= 0) return rc;
@@ -1181,6 +1273,7 @@ static int enqueue_token(xalm_cuda_model* m, int mode, cudaStream_t s, int* n_la
 		da.n_phases = m->n_phases[mode];
 		da.tl = tune("mega_timeline") ? m->d_mega_tl : nullptr;
 		da.tl_phases = m->n_phases[XALM_OUTPUT_LOGITS];
+		da.quiet = tune("mega_quiet");
 		e = dm_launch(m->dm_type, da, m->dm_grid, m->dm_smem, s, tune("mega_coop") != 0);
 		if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "token kernel launch failed: %s", cudaGetErrorString(e));
 		nl++;
