@@ -152,12 +152,12 @@ def iter_tensors(c: dict, wtype: T.XType, seed: int = 0, std: float = 0.02, norm
     yield ones("output.norm.weight")
 
 
-def write_checkpoint(path: str, shape: str, wtype: str, seed: int = 0, **over) -> dict:
+def write_checkpoint(path: str, shape: str, wtype: str, seed: int = 0, std: float = 0.02, **over) -> dict:
     """Write a complete .xalm (weights + tokenizer.tokens) for `shape` in format `wtype`; returns the config."""
     c = model_config(shape, **over)
     t = T.parse(wtype)
     tensors = OrderedDict()
-    for name, xt, arr in iter_tensors(c, t, seed):
+    for name, xt, arr in iter_tensors(c, t, seed, std=std):
         tensors[name] = (xt.name.lower(), arr)
     toks = b"".join(tok + b"\x00" for tok in byte_fallback_tokens(c["vocab_size"]))
     tensors["tokenizer.tokens"] = ("u8", np.frombuffer(toks, dtype=np.uint8))
