@@ -154,17 +154,20 @@ def run_reference(args):
     tensors = {name: (t.id, np.ascontiguousarray(arr).view(np.uint8).reshape(-1)) for name, t, arr in synth.iter_tensors(cfg_full, wtype, args.seed)}
     gen_s = time.time() - t0
     om = oracle.OracleModel(cfg, tensors, acc_mode=1)
+    # the SAME positions as the GPU arm: spread uniformly over [0, ctx) (attention walks kv_len = pos + 1 rows of the fp16 ring)
+    pos_list = positions_for(args.steps, cfg["max_seq_len"])
     tok = 1
     for i in range(args.warmup):
-        lg = om.forward(tok, i, 1)
+        lg = om.forward(tok, pos_list[min(i, len(pos_list) - 1)], 1)
         tok = oracle.sample_argmax(lg)
     t0 = time.perf_counter()
     for i in range(args.steps):
-        lg = om.forward(tok, args.warmup + i, 1)
+        lg = om.forward(tok, pos_list[i], 1)
         tok = oracle.sample_argmax(lg)
     dt = time.perf_counter() - t0
     tps = args.steps / dt
-    sample = f"{args.steps} greedy tokens at positions {args.warmup}..{args.warmup + args.steps - 1} of the same {args.shape} {args.wtype} model (full depth), wall clock"
+    sample = (f"{args.steps} tokens at positions spread uniformly over [0, {cfg['max_seq_len']}) — the GPU arm's positions — of the same "
+              f"{args.shape} {args.wtype} model (full depth), wall clock")
     line = {
         "impl": "reference", "metric": "decode_tokens_per_s", "value": tps, "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -385,6 +388,8 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-tokens", type=int, default=6, help="tokens the CPU baseline decodes (rank 0, N=1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the greedy-token parity check against the CPU oracle after the timed region")
+    ap.add_argument("--parity-tokens", type=int, default=8)
     ap.add_argument("--layers", type=int, default=0, help="depth-reduced variant of --shape (stated in config.workload); 0 = full depth")
     ap.add_argument("--past-window", action="store_true",
                     help="also time steps at positions >= ctx: the KV ring is full (kv_len = ctx), 2 attention sinks active (infer.cpp:608-613)")
@@ -442,7 +447,7 @@ def main():
     tstream = torch.cuda.Stream()
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
-    keep_host = (world == 1 and rank == 0 and not args.no_cpu_baseline)
+    keep_host = rank == 0 and not args.no_parity      # rank 0 keeps the full checkpoint: parity check at every N, CPU baseline at N = 1
     t0 = time.time()
     ipc_exchange = None
     if world > 1 and os.environ.get("XALM_TP_PEER", "1") != "0":
@@ -520,6 +525,39 @@ def main():
                 "value": n / (pms / 1e3), "unit": "tok/s", "ms_per_step": pms / n, "bytes_per_step_this_rank": pb,
                 "achieved_gbs_this_rank": pb * n / (pms / 1e3) / 1e9}
 
+    # ---- parity, in the record the driver keeps: the (sharded) model and the CPU oracle decode the same prompt greedily ----
+    parity = None
+    if not args.no_parity:
+        prompt = [1] + [int(t) for t in np.random.default_rng(7).integers(3, cfg["vocab_size"], size=3)]
+        pstate = InferenceState(cfg).cuda()
+        psampler = Sampler(cfg)
+        om = None
+        if rank == 0:
+            from oracle import oracle
+            oracle.set_threads(max(1, (os.cpu_count() or 1)))
+            om = oracle.OracleModel(cfg, host_tensors, acc_mode=1)
+        lg_o = None
+        for p_, t_ in enumerate(prompt):
+            last = p_ + 1 == len(prompt)
+            model.forward(pstate, t_, p_, 1 if last else 0)
+            if om:
+                lg_o = om.forward(t_, p_, 1 if last else 0)
+        seq_g, seq_o, worst = list(prompt), list(prompt), 0.0
+        for _ in range(args.parity_tokens):
+            tg = psampler.sample_argmax(pstate)
+            if om:
+                worst = max(worst, float(np.max(np.abs(pstate.logits() - lg_o))))
+                to = oracle.sample_argmax(lg_o)
+                seq_o.append(to)
+                lg_o = om.forward(to, len(seq_o) - 1, 1)
+            seq_g.append(tg)
+            model.forward(pstate, tg, len(seq_g) - 1, 1)
+        if om:
+            om.close()
+            parity = {"tokens_match": seq_g == seq_o, "max_abs_logit": worst, "tolerance": 1e-2, "greedy_tokens": args.parity_tokens,
+                      "prompt_tokens": len(prompt), "against": "oracle/liboracle.so on rank 0 (restatement of src/infer.cpp, itself pinned to the "
+                      "reference's own C++ by tests/golden/ref_fwd_*.npz), same checkpoint, full depth", "tokens": seq_g[len(prompt):]}
+
     # ---- roofline: whole step, and the dominant kernel (fused norm + gate|up matvec) timed alone ----
     peak, peak_src = measured_peak_gbs()
     step_bytes = float(np.mean([model.active_bytes(p) for p in pos_list]))          # this rank's shard
@@ -529,17 +567,19 @@ def main():
     nbuf = max(2, int(np.ceil(600e6 / k_bytes)))
     k_ms = capi.bench_matvec(wtype.id, cfg["dim"], hidden_l, nbuf, 200, epi=2, with_norm=True)
     k_gbs = k_bytes / (k_ms / 1e3) / 1e9
+    idp_kernel = args.wtype in ("q8_0", "q8", "q4_0", "q4_1", "q5_0", "q5_1") and cfg["dim"] % 256 == 0 and (2 * hidden_l) % 8 == 0
     traffic = None
     prof = os.path.join(ROOT, "profiles", "kernel_traffic.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get(f"{args.shape}_{args.wtype}_w13_bytes")
+            traffic = json.load(open(prof)).get(f"{args.shape}_{args.wtype}_w13_idp_tp{world}_bytes")   # null unless captured for this kernel AND shard
         except Exception:
             traffic = None
 
     line = {
         "metric": "decode_tokens_per_s", "value": tps, "unit": "tok/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32 activations and accumulation; integer weight formats multiply in int8 (dp4a) against 3 x int8 block-floating activation limbs" if idp_kernel else "f32",
         "data": "synthetic", "config": workload_config(args, cfg),
         "e2e": {"value": e2e_tps, "unit": "tok/s", "h2d_bytes_per_step": 32, "d2h_bytes_per_step": cfg["vocab_size"] * 4,
                 "device_sampler": {"value": args.steps / e2e_dev_s, "unit": "tok/s", "d2h_bytes_per_step": 4,
@@ -547,7 +587,8 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks.summary(),
         "roofline": {"bound": "hbm", "achieved": k_gbs, "peak": peak, "unit": "GB/s", "frac": k_gbs / peak, "traffic": traffic,
-                     "kernel": f"matvec_kernel<{args.wtype}, norm+gate|up+GLU> {2 * hidden_l}x{cfg['dim']}", "bytes_per_launch": k_bytes,
+                     "kernel": f"matvec_idp_kernel<{args.wtype}, norm> (norm + gate|up + GLU) {2 * hidden_l}x{cfg['dim']}" if idp_kernel else
+                               f"matvec_tma_kernel<{args.wtype}, norm> (norm + gate|up + GLU) {2 * hidden_l}x{cfg['dim']}", "bytes_per_launch": k_bytes,
                      "ms_per_launch": k_ms, "peak_source": peak_src, "timing": "CUDA events around 200 back-to-back launches on rotating buffers > L2"},
         "step_roofline": {"bytes_per_step": step_bytes, "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
                           "frac_of_8000": step_gbs / 8000.0, "formula": "Model::active_bytes(pos) (model.cpp:12-35), mean over the timed positions"},
@@ -555,6 +596,8 @@ def main():
     }
     if past:
         line["past_window"] = past
+    if parity is not None:
+        line["parity"] = parity
 
     # ---- BASELINE config[2] beside it (N = 1): the batched prefill / perplexity pass on the same resident model ----
     if world == 1 and not args.no_prefill and cfg["head_dim"] in (64, 128):
@@ -564,21 +607,22 @@ def main():
             line["perplexity_mode"] = {"error": str(ex)[:200]}
 
     # ---- CPU baseline beside it: the oracle port on the host cores, same weights (rank 0, N = 1 only) ----
-    if keep_host:
+    if keep_host and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle
         cpu_cores = oracle.set_threads(os.cpu_count() or 1)
         om = oracle.OracleModel(cfg, host_tensors, acc_mode=1)
         tok = 1
         lg = om.forward(tok, 0, 1)          # warm-up (touches every page)
-        t0 = time.perf_counter()
         n = args.cpu_tokens
+        cpos = positions_for(n, ctx)        # spread over the context like the timed GPU steps
+        t0 = time.perf_counter()
         for i in range(n):
             tok = oracle.sample_argmax(lg)
-            lg = om.forward(tok, 1 + i, 1)
+            lg = om.forward(tok, cpos[i], 1)
         cdt = time.perf_counter() - t0
         om.close()
         line["cpu_baseline"] = {"value": n / cdt, "unit": "tok/s", "cores": cpu_cores, "kind": "port",
-                                "sample": f"{n} greedy tokens at positions 1..{n} of the same model (full depth, same weights), wall clock"}
+                                "sample": f"{n} tokens at positions spread uniformly over [0, {ctx}) of the same model (full depth, same weights), wall clock"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     model.close()

@@ -29,7 +29,7 @@ def main():
     gm = Model.from_tensors(cfg, tensors).cuda(device=local, tp_rank=rank, tp_size=world, comm_id=comm_id,
                                                ipc_exchange=tp.make_ipc_exchange(dist, world) if use_peer else None)
     state, sampler = InferenceState(cfg).cuda(), Sampler(cfg)
-    prompt = [int(t) for t in np.random.default_rng(0).integers(3, cfg["vocab_size"], size=40)]
+    prompt = [int(t) for t in np.random.default_rng(0).integers(3, cfg["vocab_size"], size=int(os.environ.get("XALM_TP_PROMPT", "40")))]
     om = None
     if rank == 0:
         from oracle import oracle

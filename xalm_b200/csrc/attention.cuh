@@ -37,6 +37,11 @@ struct AttnArgs {
 	unsigned long long pf_bytes;
 };
 
+// K/V rows: coherent L2 loads (ld.global.cg).  NOT the read-only path: row kv_pos and the sink rows are written by the QKV
+// kernel that may still be running when this kernel's early batch is requested (PDL), and ld.global.nc is only defined for data
+// that nobody writes during the kernel's lifetime.
+__device__ __forceinline__ uint4 ld_kv16(const __half* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
+
 __host__ __device__ inline int attn_split_len(int kv_len, int n_splits, int min_split) {
 	int len = (kv_len + n_splits - 1) / n_splits;
 	if (len < min_split) len = min_split;
@@ -83,8 +88,8 @@ __global__ void __launch_bounds__(NW * 32) attn_decode_kernel(const AttnArgs a) 
 		for (int j = 0; j < TB; j++) {
 			const int t = tb + j * RPW + sub;
 			const int tc = t < t1 ? t : t0;
-			kn[j] = ld_stream16(kbase + (size_t) tc * kv_stride);
-			vn[j] = ld_stream16(vbase + (size_t) tc * kv_stride);
+			kn[j] = ld_kv16(kbase + (size_t) tc * kv_stride);
+			vn[j] = ld_kv16(vbase + (size_t) tc * kv_stride);
 		}
 	};
 	const int tb_first = t0 + warp * RPW * TB;
@@ -116,8 +121,8 @@ __global__ void __launch_bounds__(NW * 32) attn_decode_kernel(const AttnArgs a) 
 		for (int j = 0; j < TB; j++) {
 			const int t = tb_first + j * RPW + sub;
 			if (t < t1 && (t == kv_pos || t < kv_sink)) {
-				kn[j] = ld_stream16(kbase + (size_t) t * kv_stride);
-				vn[j] = ld_stream16(vbase + (size_t) t * kv_stride);
+				kn[j] = ld_kv16(kbase + (size_t) t * kv_stride);
+				vn[j] = ld_kv16(vbase + (size_t) t * kv_stride);
 			}
 		}
 	} else if (tb_first < t1) fetch(tb_first);

@@ -36,6 +36,9 @@ SHAPES = {
     # every per-rank dimension stays a multiple of 256 up to TP=4 (the fused exchange rides on the TMA matvec kernels)
     "tp": dict(dim=1024, hidden_dim=3072, head_dim=128, n_layers=4, n_heads=8, n_kv_heads=4, vocab_size=4096,
                max_seq_len=1024, rope_theta=10000.0, arch="LlamaForCausalLM"),
+    # TP=8: one kv head and 256 q / 768 hidden / 512 vocab columns per rank
+    "tp8": dict(dim=2048, hidden_dim=6144, head_dim=128, n_layers=2, n_heads=16, n_kv_heads=8, vocab_size=4096,
+                max_seq_len=512, rope_theta=10000.0, arch="LlamaForCausalLM"),
     "small": dict(dim=1024, hidden_dim=2816, head_dim=128, n_layers=4, n_heads=8, n_kv_heads=2, vocab_size=4096,
                   max_seq_len=1024, rope_theta=10000.0, arch="LlamaForCausalLM"),
 }
@@ -119,6 +122,8 @@ def metadata_strings(c: dict) -> OrderedDict:
     md["norm_type"] = "rmsnorm"
     md["act_type"] = c["act_type"]
     md["tie_word_embeddings"] = str(bool(c["tie_word_embeddings"]))
+    if "qkv_clip" in c:
+        md["qkv_clip"] = str(c["qkv_clip"])   # optional key (model.h:84-85)
     return md
 
 
