@@ -102,7 +102,7 @@ def positions_for(steps: int, ctx: int) -> list:
     return [int(round(i * (ctx - 1) / (steps - 1))) for i in range(steps)]
 
 
-def build_model_streaming(cfg_full: dict, cfg: dict, wtype, seed: int, keep_host: bool, **cuda_kw):
+def build_model_streaming(cfg_full: dict, cfg: dict, wtype, seed: int, keep_host: bool, std: float = 0.02, **cuda_kw):
     """Generate the synthetic checkpoint tensor by tensor and upload each as it is made (peak host RAM = one tensor
     unless keep_host, which the CPU baseline needs)."""
     import ctypes as C
@@ -129,11 +129,16 @@ def build_model_streaming(cfg_full: dict, cfg: dict, wtype, seed: int, keep_host
     from xalm_b200 import xalm_file as X
     shapes = X.expected_tensors(cfg)
     host = {}
-    for name, t, arr in synth.iter_tensors(cfg_full, wtype, seed):
-        raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
-        model.upload(name, t, shapes[name], raw)
-        if keep_host:
-            host[name] = (t.id, raw)
+    if model.tp_size > 1 and not keep_host:
+        # shard-aware: this rank generates, quantises and uploads only the rows / columns it keeps (1/P of the host work and memory)
+        for name, t, arr, rng in synth.iter_tensors(cfg_full, wtype, seed, std=std, shard_range=model.shard_range):
+            model.upload_shard(name, t, shapes[name], rng, np.ascontiguousarray(arr).view(np.uint8).reshape(-1))
+    else:
+        for name, t, arr in synth.iter_tensors(cfg_full, wtype, seed, std=std):
+            raw = np.ascontiguousarray(arr).view(np.uint8).reshape(-1)
+            model.upload(name, t, shapes[name], raw)
+            if keep_host:
+                host[name] = (t.id, raw)
     capi.check(L.xalm_cuda_finalize(h))
     return model, host
 

@@ -87,6 +87,13 @@ int xalm_cuda_create(const xalm_config* cfg, int device, int tp_rank, int tp_siz
  * only this rank's shard.  The host buffer may be freed on return. */
 int xalm_cuda_upload_tensor(xalm_cuda_model* m, const char* name, int type_id, const int* shape, int rank,
                             const void* data, size_t nbytes);
+/* Shard-aware upload for tensor-parallel handles, so that a rank reads / generates only what it keeps (the reference loader it
+ * stands in for reads every tensor whole, model.cpp:48-118).  xalm_cuda_shard_range: range4 = {row0, row1, col0, col1} of the
+ * ELEMENT shape this rank keeps of tensor `name` (norms and the embedding table: everything).  xalm_cuda_upload_tensor_shard:
+ * `data` holds exactly that block, dense, in on-disk bytes (rows of (col1 - col0) elements); `shape` is still the full shape. */
+int xalm_cuda_shard_range(xalm_cuda_model* m, const char* name, int* range4);
+int xalm_cuda_upload_tensor_shard(xalm_cuda_model* m, const char* name, int type_id, const int* shape, int rank, const int* range4,
+                                  const void* data, size_t nbytes);
 /* Checks every tensor arrived, builds fused/concatenated device layouts, captures the per-token CUDA graphs. */
 int xalm_cuda_finalize(xalm_cuda_model* m);
 void xalm_cuda_destroy(xalm_cuda_model* m);

@@ -37,6 +37,19 @@ def test_tp_matches_oracle(world, wtype, shape):
     assert "tokens match" in r.stdout
 
 
+@pytest.mark.parametrize("world,wtype,shape", [(2, "q8_0", "tp"), (2, "q4_0", "small"), (4, "q8_0", "tp")])
+def test_tp_shard_aware_upload(world, wtype, shape):
+    """Ranks > 0 generate, quantise and upload only their shard (xalm_cuda_shard_range / xalm_cuda_upload_tensor_shard)."""
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    env = dict(os.environ, XALM_TP_SHARD="1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+                        "--master-port", "29613", os.path.join(ROOT, "tests", "tp_gpu_worker.py"), wtype, shape],
+                       capture_output=True, text=True, timeout=900, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "tokens match" in r.stdout
+
+
 def test_tp2_long_hydrate_prompt():
     """120 HYDRATE tokens before the first logits: 120 drained exchanges in a row (the protocol hole of round 1 was here)."""
     if _ngpu() < 2:

@@ -113,3 +113,16 @@ def test_shard_plan_partitions_every_tensor():
             assert np.all(cover == 1), name
     with pytest.raises(ValueError):
         tp.shard_ranges("l.0.attn.q.weight", cfg, 0, 3)                  # 2 kv heads do not split 3 ways
+
+
+def test_shard_generation_matches_the_full_tensor():
+    """A tensor-parallel rank that generates only its rows / columns (synth.normal_block) gets the bytes the full tensor has there."""
+    import numpy as np
+    from xalm_b200 import synth, types as T
+    rows, cols = 64, 1024
+    for t in (T.Q8_0, T.Q4_0, T.Q5_1, T.F16, T.BF16):
+        full = np.ascontiguousarray(synth.quantize(t, synth.normal(3, 77, rows * cols, 0.02).reshape(rows, cols))).view(np.uint8).reshape(rows, -1)
+        bpr = full.shape[1]
+        for (r0, r1, c0, c1) in ((16, 48, 0, cols), (0, rows, 256, 768), (8, 16, 512, 1024)):
+            blk = np.ascontiguousarray(synth.quantize(t, synth.normal_block(3, 77, cols, r0, r1, c0, c1, 0.02))).view(np.uint8).reshape(r1 - r0, -1)
+            assert np.array_equal(full[r0:r1, bpr * c0 // cols: bpr * c1 // cols], blk), (t.name, r0, r1, c0, c1)

@@ -23,17 +23,25 @@ def main():
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     c = synth.model_config(shape)
     cfg = X.parse_config(synth.metadata_strings(c))
-    tensors = list(synth.iter_tensors(c, T.parse(wtype), seed=1, std=0.03))
     comm_id = tp.broadcast_comm_id(dist, rank, device="cuda")
     use_peer = os.environ.get("XALM_TP_PEER", "1") != "0"
-    gm = Model.from_tensors(cfg, tensors).cuda(device=local, tp_rank=rank, tp_size=world, comm_id=comm_id,
-                                               ipc_exchange=tp.make_ipc_exchange(dist, world) if use_peer else None)
+    ipc = tp.make_ipc_exchange(dist, world) if use_peer else None
+    if os.environ.get("XALM_TP_SHARD") == "1":
+        # shard-aware upload: ranks > 0 generate and upload only what they keep (xalm_cuda_upload_tensor_shard); rank 0 builds the
+        # whole checkpoint because it also feeds the CPU oracle
+        import bench
+        gm, host = bench.build_model_streaming(c, cfg, T.parse(wtype), 1, rank == 0, std=0.03, device=local, tp_rank=rank, tp_size=world,
+                                               comm_id=comm_id, ipc_exchange=ipc)
+        tensors = None
+    else:
+        tensors = list(synth.iter_tensors(c, T.parse(wtype), seed=1, std=0.03))
+        gm = Model.from_tensors(cfg, tensors).cuda(device=local, tp_rank=rank, tp_size=world, comm_id=comm_id, ipc_exchange=ipc)
     state, sampler = InferenceState(cfg).cuda(), Sampler(cfg)
     prompt = [int(t) for t in np.random.default_rng(0).integers(3, cfg["vocab_size"], size=int(os.environ.get("XALM_TP_PROMPT", "40")))]
     om = None
     if rank == 0:
         from oracle import oracle
-        om = oracle.OracleModel(cfg, {n: (t.id, np.ascontiguousarray(a).view(np.uint8).reshape(-1)) for n, t, a in tensors})
+        om = oracle.OracleModel(cfg, host if tensors is None else {n: (t.id, np.ascontiguousarray(a).view(np.uint8).reshape(-1)) for n, t, a in tensors})
     lg_o = None
     for pos, tok in enumerate(prompt):
         mode = 1 if pos + 1 == len(prompt) else 0

@@ -1456,8 +1456,18 @@ int prefill_run(const PrefillModel& pm, PrefillScratch** scratch, const int* tok
 	if (c.head_dim != 64 && c.head_dim != 128) return set_error(XALM_ERR_UNSUPPORTED, "prefill: head_dim %d (64 or 128)", c.head_dim);
 	if (c.dim % 16 || c.hidden_dim % 16 || pm.q_dim % 16 || pm.kv_dim % 16) return set_error(XALM_ERR_UNSUPPORTED, "prefill: dims must be multiples of 16");
 	if (targets && want_logits != 2) return set_error(XALM_ERR_INVALID, "prefill: target probabilities need the logits of every position");
+	if (want_logits < 0 || want_logits > 2) return set_error(XALM_ERR_INVALID, "prefill: want_logits = %d", want_logits);
 	for (int i = 0; i < n; i++)
 		if (tokens[i] < 0 || tokens[i] >= c.vocab_size) return set_error(XALM_ERR_INVALID, "prefill: token %d out of range", tokens[i]);
+	// everything that can be refused is refused HERE, before anything is enqueued: an error return must not leave half a pass in
+	// flight on two streams and a partly overwritten KV cache
+	if (targets)
+		for (int i = 0; i < n; i++)
+			if (targets[i] < 0 || targets[i] >= c.vocab_size) return set_error(XALM_ERR_INVALID, "prefill: target %d out of range", targets[i]);
+	for (const PrefillLayer& P : pm.layers)
+		if (!prefill_type_ok(P.wqkv.type) || !prefill_type_ok(P.wo.type) || !prefill_type_ok(P.w13.type) || !prefill_type_ok(P.w2.type))
+			return set_error(XALM_ERR_UNSUPPORTED, "prefill: weight type %d", P.wqkv.type);
+	if (want_logits && !prefill_type_ok(pm.wcls.type)) return set_error(XALM_ERR_UNSUPPORTED, "prefill: weight type %d", pm.wcls.type);
 	// split: 1 = fp16 x fp16; 2 = hi+lo activations; 3 = hi+lo activations AND weights AND attention operands (fp32-grade)
 	const int na = split >= 2 ? 2 : 1;
 	const bool precise = split >= 3;

@@ -1038,8 +1038,65 @@ int xalm_cuda_comm_init(xalm_cuda_model* m, const void* id128) {
 	return XALM_OK;
 }
 
+// the rows / columns of tensor `piece` (full element shape er x ec) that rank R of P keeps
+static void shard_range_of(const xalm_cuda_model* m, int piece, int er, int ec, int* r0, int* r1, int* c0, int* c1) {
+	const int R = m->tp_rank;
+	*r0 = 0; *r1 = er; *c0 = 0; *c1 = ec;
+	switch (piece) {
+		case 102: *r0 = R * m->vocab_l; *r1 = (R + 1) * m->vocab_l; break;                       // classifier: vocab rows
+		case 100: break;                                                                          // embedding: replicated (gathered by row)
+		case P_Q: *r0 = R * m->q_dim_l; *r1 = (R + 1) * m->q_dim_l; break;                        // heads
+		case P_K: case P_V: *r0 = R * m->kv_dim_l; *r1 = (R + 1) * m->kv_dim_l; break;            // kv heads
+		case P_O: *c0 = R * m->q_dim_l; *c1 = (R + 1) * m->q_dim_l; break;                        // input (quantised) axis
+		case P_GATE: case P_UP: *r0 = R * m->hidden_l; *r1 = (R + 1) * m->hidden_l; break;
+		case P_DOWN: *c0 = R * m->hidden_l; *c1 = (R + 1) * m->hidden_l; break;
+	}
+}
+
+static int expected_shape(const xalm_cuda_model* m, int piece, int* er, int* ec, bool* is_norm) {
+	const xalm_config& c = m->c;
+	*er = 0; *ec = 0; *is_norm = false;
+	switch (piece) { // model.cpp:83-114
+		case 100: case 102: *er = c.vocab_size; *ec = c.dim; break;
+		case 101: case P_ATT_NORM: case P_FFN_NORM: *er = c.dim; *is_norm = true; break;
+		case P_Q: *er = m->q_dim; *ec = c.dim; break;
+		case P_K: case P_V: *er = m->kv_dim; *ec = c.dim; break;
+		case P_O: *er = c.dim; *ec = m->q_dim; break;
+		case P_GATE: case P_UP: *er = c.hidden_dim; *ec = c.dim; break;
+		case P_DOWN: *er = c.dim; *ec = c.hidden_dim; break;
+		default: return set_error(XALM_ERR_INVALID, "unknown tensor");
+	}
+	return XALM_OK;
+}
+
+int xalm_cuda_shard_range(xalm_cuda_model* m, const char* name, int* range4) {
+	if (!m || !name || !range4) return set_error(XALM_ERR_INVALID, "NULL argument");
+	int layer, piece, er, ec;
+	bool is_norm;
+	XALM_TRY(parse_tensor_name(name, m->c.n_layers, &layer, &piece));
+	XALM_TRY(expected_shape(m, piece, &er, &ec, &is_norm));
+	if (is_norm) { range4[0] = 0; range4[1] = er; range4[2] = 0; range4[3] = 1; return XALM_OK; }
+	shard_range_of(m, piece, er, ec, &range4[0], &range4[1], &range4[2], &range4[3]);
+	if (piece == 100 && m->c.tie_word_embeddings) { range4[0] = 0; range4[1] = er; } // also feeds the classifier shard: keep it whole
+	return XALM_OK;
+}
+
+static int upload_impl(xalm_cuda_model* m, const char* name, int type_id, const int* shape, int rank, const void* data, size_t nbytes,
+                       const int* sub /* NULL = data is the full tensor; else {r0, r1, c0, c1} = the block data holds */);
+
 int xalm_cuda_upload_tensor(xalm_cuda_model* m, const char* name, int type_id, const int* shape, int rank, const void* data,
                             size_t nbytes) {
+	return upload_impl(m, name, type_id, shape, rank, data, nbytes, nullptr);
+}
+
+int xalm_cuda_upload_tensor_shard(xalm_cuda_model* m, const char* name, int type_id, const int* shape, int rank, const int* range4,
+                                  const void* data, size_t nbytes) {
+	if (!range4) return set_error(XALM_ERR_INVALID, "NULL argument");
+	return upload_impl(m, name, type_id, shape, rank, data, nbytes, range4);
+}
+
+static int upload_impl(xalm_cuda_model* m, const char* name, int type_id, const int* shape, int rank, const void* data, size_t nbytes,
+                       const int* sub) {
 	if (!m || !name || !shape || !data) return set_error(XALM_ERR_INVALID, "NULL argument");
 	if (m->finalized) return set_error(XALM_ERR_STATE, "upload after finalize");
 	XALM_CUDA_CHECK(cudaSetDevice(m->device));
@@ -1048,26 +1105,33 @@ int xalm_cuda_upload_tensor(xalm_cuda_model* m, const char* name, int type_id, c
 	XALM_TRY(parse_tensor_name(name, c.n_layers, &layer, &piece));
 	TypeInfo ti;
 	if (!type_info(type_id, &ti)) return set_error(XALM_ERR_INVALID, "invalid type: %d", type_id);
-	// expected element shapes: model.cpp:83-114
 	int er = 0, ec = 0;
 	bool is_norm = false;
-	switch (piece) {
-		case 100: case 102: er = c.vocab_size; ec = c.dim; break;
-		case 101: case P_ATT_NORM: case P_FFN_NORM: er = c.dim; is_norm = true; break;
-		case P_Q: er = m->q_dim; ec = c.dim; break;
-		case P_K: case P_V: er = m->kv_dim; ec = c.dim; break;
-		case P_O: er = c.dim; ec = m->q_dim; break;
-		case P_GATE: case P_UP: er = c.hidden_dim; ec = c.dim; break;
-		case P_DOWN: er = c.dim; ec = c.hidden_dim; break;
-	}
+	XALM_TRY(expected_shape(m, piece, &er, &ec, &is_norm));
 	if ((is_norm && (rank != 1 || shape[0] != er)) || (!is_norm && (rank != 2 || shape[0] != er || shape[1] != ec))) {
 		if (rank == 2) return set_error(XALM_ERR_INVALID, "shape mismatch for %s: [%d, %d] vs [%d, %d] expected!", name, shape[0], shape[1], er, ec);
 		return set_error(XALM_ERR_INVALID, "shape mismatch for %s: rank %d, [%d] vs [%d] expected!", name, rank, shape[0], er);
 	}
-	const size_t elems = is_norm ? (size_t) er : (size_t) er * ec;
+	size_t elems = is_norm ? (size_t) er : (size_t) er * ec;
 	if (elems % ti.block || (!is_norm && ec % ti.block)) return set_error(XALM_ERR_INVALID, "%s: row length %d is not a multiple of the block size %d", name, ec, ti.block);
+	// shard upload: `data` holds only rows [sr0, sr1) x columns [sc0, sc1) of the tensor, which must be exactly what this rank keeps
+	int sr0 = 0, sr1 = er, sc0 = 0, sc1 = ec;
+	if (sub && !is_norm) {
+		int need[4];
+		XALM_TRY(xalm_cuda_shard_range(m, name, need));
+		if (sub[0] != need[0] || sub[1] != need[1] || sub[2] != need[2] || sub[3] != need[3])
+			return set_error(XALM_ERR_INVALID, "%s: rank %d keeps rows [%d, %d) x columns [%d, %d), the upload holds [%d, %d) x [%d, %d)", name, m->tp_rank,
+			                 need[0], need[1], need[2], need[3], sub[0], sub[1], sub[2], sub[3]);
+		sr0 = sub[0]; sr1 = sub[1]; sc0 = sub[2]; sc1 = sub[3];
+		if ((sc1 - sc0) % ti.block) return set_error(XALM_ERR_INVALID, "%s: column range splits a block", name);
+		elems = (size_t) (sr1 - sr0) * (sc1 - sc0);
+	}
 	if (nbytes != elems / ti.block * ti.bytes) return set_error(XALM_ERR_INVALID, "buffer size mismatch for %s: %zu vs %zu", name, nbytes, elems / ti.block * ti.bytes);
 	const uint8_t* host = (const uint8_t*) data;
+	// geometry of `host`: its rows are (sc1 - sc0) elements long and its first row / column is (sr0, sc0) of the tensor
+	auto put = [&](WMat& w, int dst_row, int r0, int r1, int c0, int c1) -> int {
+		return upload_piece(w, dst_row, type_id, host, sc1 - sc0, r0 - sr0, r1 - sr0, c0 - sc0, c1 - sc0, m->staging, m->stream);
+	};
 	cudaStream_t s = m->stream;
 	const int P = m->tp_size, R = m->tp_rank;
 
@@ -1097,6 +1161,7 @@ int xalm_cuda_upload_tensor(xalm_cuda_model* m, const char* name, int type_id, c
 	if (piece == 100 || piece == 102) {
 		if (piece == 100) {
 			// embedding table: replicated, kept in on-disk layout for the row gather
+			if (sr0 != 0 || sr1 != er) return set_error(XALM_ERR_INVALID, "embed.weight is replicated: upload all of its rows");
 			XALM_TRY(m->da.alloc((void**) &m->embed_raw, nbytes));
 			XALM_CUDA_CHECK(cudaMemcpy(m->embed_raw, host, nbytes, cudaMemcpyHostToDevice));
 			m->embed_type = type_id;
@@ -1108,7 +1173,7 @@ int xalm_cuda_upload_tensor(xalm_cuda_model* m, const char* name, int type_id, c
 			return XALM_OK; // ignored, like the reference (model.cpp:112-114 loads embed.weight instead)
 		}
 		XALM_TRY(ensure(m->wcls, m->vocab_l, c.dim));
-		XALM_TRY(upload_piece(m->wcls.m, 0, type_id, host, c.dim, R * m->vocab_l, (R + 1) * m->vocab_l, 0, c.dim, m->staging, s));
+		XALM_TRY(put(m->wcls.m, 0, R * m->vocab_l, (R + 1) * m->vocab_l, 0, c.dim));
 		m->got_cls = true;
 		return XALM_OK;
 	}
@@ -1118,31 +1183,31 @@ int xalm_cuda_upload_tensor(xalm_cuda_model* m, const char* name, int type_id, c
 	switch (piece) {
 		case P_Q:
 			XALM_TRY(ensure(L.wqkv, m->q_dim_l + 2 * m->kv_dim_l, c.dim));
-			XALM_TRY(upload_piece(L.wqkv.m, 0, type_id, host, c.dim, R * m->q_dim_l, (R + 1) * m->q_dim_l, 0, c.dim, m->staging, s));
+			XALM_TRY(put(L.wqkv.m, 0, R * m->q_dim_l, (R + 1) * m->q_dim_l, 0, c.dim));
 			break;
 		case P_K:
 			XALM_TRY(ensure(L.wqkv, m->q_dim_l + 2 * m->kv_dim_l, c.dim));
-			XALM_TRY(upload_piece(L.wqkv.m, m->q_dim_l, type_id, host, c.dim, R * m->kv_dim_l, (R + 1) * m->kv_dim_l, 0, c.dim, m->staging, s));
+			XALM_TRY(put(L.wqkv.m, m->q_dim_l, R * m->kv_dim_l, (R + 1) * m->kv_dim_l, 0, c.dim));
 			break;
 		case P_V:
 			XALM_TRY(ensure(L.wqkv, m->q_dim_l + 2 * m->kv_dim_l, c.dim));
-			XALM_TRY(upload_piece(L.wqkv.m, m->q_dim_l + m->kv_dim_l, type_id, host, c.dim, R * m->kv_dim_l, (R + 1) * m->kv_dim_l, 0, c.dim, m->staging, s));
+			XALM_TRY(put(L.wqkv.m, m->q_dim_l + m->kv_dim_l, R * m->kv_dim_l, (R + 1) * m->kv_dim_l, 0, c.dim));
 			break;
 		case P_O: // row-split under TP = slice of the INPUT (quantised) axis
 			XALM_TRY(ensure(L.wo, c.dim, m->q_dim_l));
-			XALM_TRY(upload_piece(L.wo.m, 0, type_id, host, m->q_dim, 0, c.dim, R * m->q_dim_l, (R + 1) * m->q_dim_l, m->staging, s));
+			XALM_TRY(put(L.wo.m, 0, 0, c.dim, R * m->q_dim_l, (R + 1) * m->q_dim_l));
 			break;
 		case P_GATE:
 			XALM_TRY(ensure(L.w13, 2 * m->hidden_l, c.dim));
-			XALM_TRY(upload_piece(L.w13.m, 0, type_id, host, c.dim, R * m->hidden_l, (R + 1) * m->hidden_l, 0, c.dim, m->staging, s));
+			XALM_TRY(put(L.w13.m, 0, R * m->hidden_l, (R + 1) * m->hidden_l, 0, c.dim));
 			break;
 		case P_UP:
 			XALM_TRY(ensure(L.w13, 2 * m->hidden_l, c.dim));
-			XALM_TRY(upload_piece(L.w13.m, m->hidden_l, type_id, host, c.dim, R * m->hidden_l, (R + 1) * m->hidden_l, 0, c.dim, m->staging, s));
+			XALM_TRY(put(L.w13.m, m->hidden_l, R * m->hidden_l, (R + 1) * m->hidden_l, 0, c.dim));
 			break;
 		case P_DOWN:
 			XALM_TRY(ensure(L.w2, c.dim, m->hidden_l));
-			XALM_TRY(upload_piece(L.w2.m, 0, type_id, host, c.hidden_dim, 0, c.dim, R * m->hidden_l, (R + 1) * m->hidden_l, m->staging, s));
+			XALM_TRY(put(L.w2.m, 0, 0, c.dim, R * m->hidden_l, (R + 1) * m->hidden_l));
 			break;
 	}
 	L.got[piece] = true;
@@ -1447,6 +1512,8 @@ int xalm_cuda_finalize(xalm_cuda_model* m) {
 		for (int p = 0; p < 9; p++)
 			if (!m->layers[l].got[p]) return set_error(XALM_ERR_STATE, "missing tensor l.%d.%s.weight", l, names[p]);
 	if (m->tp_size > 1 && !m->comm) return set_error(XALM_ERR_STATE, "tp_size %d but xalm_cuda_comm_init was not called", m->tp_size);
+	if (m->tp_size > 1 && 2 * c.n_layers > 1024)
+		return set_error(XALM_ERR_UNSUPPORTED, "tensor parallel: %d layers need %d exchange tags per token, the tag space has 1024", c.n_layers, 2 * c.n_layers);
 	if (m->staging.p) { cudaFree(m->staging.p); m->staging.p = nullptr; m->staging.cap = 0; }
 
 	auto fzero = [&](float** p, size_t n) -> int {
@@ -1484,6 +1551,8 @@ int xalm_cuda_finalize(xalm_cuda_model* m) {
 	XALM_CUDA_CHECK(cudaMemcpy(m->rope_freq, freq.data(), freq.size() * sizeof(float), cudaMemcpyHostToDevice));
 	const int G = c.n_heads / c.n_kv_heads;
 	m->attn_splits = attn_auto_splits(m->n_kv_heads_l);
+	// the last-CTA merge parks 3 floats per (split, head) in the 8 x G x head_dim floats of the per-warp partial area (attention.cuh)
+	if (m->attn_splits > 8 * c.head_dim / 3) m->attn_splits = 8 * c.head_dim / 3;
 	XALM_TRY(fzero(&m->attn_acc, (size_t) m->n_kv_heads_l * m->attn_splits * G * c.head_dim));
 	XALM_TRY(fzero(&m->attn_ml, (size_t) m->n_kv_heads_l * m->attn_splits * G * 2));
 	XALM_TRY(m->da.alloc((void**) &m->tickets, 2 * m->n_kv_heads_l * sizeof(unsigned int))); // x2: the token kernel splits 8-head groups

@@ -129,6 +129,20 @@ class Model:
         capi.check(capi.lib().xalm_cuda_upload_tensor(self._h, name.encode(), t.id, shp, len(shape), raw.ctypes.data_as(C.c_void_p),
                                                       raw.nbytes))
 
+    def shard_range(self, name: str) -> tuple:
+        """(row0, row1, col0, col1) of the element shape this tensor-parallel rank keeps of tensor `name`."""
+        r = (C.c_int * 4)()
+        capi.check(capi.lib().xalm_cuda_shard_range(self._h, name.encode(), r))
+        return tuple(r)
+
+    def upload_shard(self, name: str, t: T.XType, shape, rng: tuple, raw: np.ndarray):
+        """Upload only the block `rng` = shard_range(name) of a tensor whose full element shape is `shape`."""
+        raw = np.ascontiguousarray(raw)
+        shp = (C.c_int * len(shape))(*shape)
+        r4 = (C.c_int * 4)(*rng)
+        capi.check(capi.lib().xalm_cuda_upload_tensor_shard(self._h, name.encode(), t.id, shp, len(shape), r4, raw.ctypes.data_as(C.c_void_p),
+                                                            raw.nbytes))
+
     @staticmethod
     def comm_unique_id() -> bytes:
         buf = (C.c_char * 128)()

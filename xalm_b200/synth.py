@@ -53,6 +53,8 @@ def host():
         L.xalm_host_quantize.argtypes = [C.c_int, C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p]
         L.xalm_host_normal.argtypes = [C.c_uint64, C.c_uint64, C.c_longlong, C.c_float, C.c_float, C.c_void_p]
         L.xalm_host_normal.restype = None
+        L.xalm_host_normal_block.argtypes = [C.c_uint64, C.c_uint64, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong, C.c_longlong,
+                                             C.c_float, C.c_float, C.c_void_p]
         L.xalm_host_set_threads.argtypes = [C.c_int]
         L.xalm_host_set_threads.restype = None
         _HOST = L
@@ -66,6 +68,14 @@ def set_threads(n: int):
 def normal(seed: int, stream: int, n: int, std: float, mean: float = 0.0) -> np.ndarray:
     out = np.empty(n, dtype=np.float32)
     host().xalm_host_normal(seed, stream, n, mean, std, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def normal_block(seed: int, stream: int, n_cols: int, r0: int, r1: int, c0: int, c1: int, std: float, mean: float = 0.0) -> np.ndarray:
+    """Rows [r0, r1) x columns [c0, c1) of the (rows, n_cols) matrix normal(seed, stream, rows * n_cols, std) would give."""
+    out = np.empty((r1 - r0, c1 - c0), dtype=np.float32)
+    if host().xalm_host_normal_block(seed, stream, n_cols, r0, r1, c0, c1, mean, std, out.ctypes.data_as(C.c_void_p)):
+        raise ValueError("normal_block: column bounds must be even")
     return out
 
 
@@ -128,18 +138,26 @@ def metadata_strings(c: dict) -> OrderedDict:
 
 
 def iter_tensors(c: dict, wtype: T.XType, seed: int = 0, std: float = 0.02, norm_type: T.XType = T.F32,
-                 embed_type: T.XType | None = None):
+                 embed_type: T.XType | None = None, shard_range=None):
     """Yield (name, XType, array-with-header-shape) in the order convert.py's load_weights emits them
-    (convert.py:825-848).  Each tensor has its own RNG stream, so any subset can be generated on its own."""
+    (convert.py:825-848).  Each tensor has its own RNG stream, so any subset can be generated on its own.
+    shard_range(name) -> (r0, r1, c0, c1): generate and quantise only that block of every matrix (what a tensor-parallel
+    rank keeps, xalm_cuda_shard_range) and yield (name, XType, block, (r0, r1, c0, c1)) — the same values the full tensor has
+    there: rows are quantised independently and column bounds are multiples of 256, so no quant block is split."""
     q_dim, kv_dim = c["n_heads"] * c["head_dim"], c["n_kv_heads"] * c["head_dim"]
     embed_type = embed_type or wtype
 
     def w(name, rows, cols, t):
+        if shard_range is not None:
+            r0, r1, c0, c1 = shard_range(name)
+            x = normal_block(seed, zlib.crc32(name.encode()), cols, r0, r1, c0, c1, std)
+            return name, t, quantize(t, x), (r0, r1, c0, c1)
         x = normal(seed, zlib.crc32(name.encode()), rows * cols, std).reshape(rows, cols)
         return name, t, quantize(t, x)
 
     def ones(name):
-        return name, norm_type, quantize(norm_type, np.ones(c["dim"], dtype=np.float32))
+        r = name, norm_type, quantize(norm_type, np.ones(c["dim"], dtype=np.float32))
+        return r + ((0, c["dim"], 0, 1),) if shard_range is not None else r
 
     yield w("embed.weight", c["vocab_size"], c["dim"], embed_type)
     for l in range(c["n_layers"]):
