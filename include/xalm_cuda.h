@@ -94,6 +94,9 @@ int xalm_cuda_upload_tensor(xalm_cuda_model* m, const char* name, int type_id, c
 int xalm_cuda_shard_range(xalm_cuda_model* m, const char* name, int* range4);
 int xalm_cuda_upload_tensor_shard(xalm_cuda_model* m, const char* name, int type_id, const int* shape, int rank, const int* range4,
                                   const void* data, size_t nbytes);
+/* Page-locked host memory for upload staging (H2D copies from it run at full PCIe rate and may be asynchronous). */
+void* xalm_cuda_host_alloc(size_t nbytes);
+void xalm_cuda_host_free(void* p);
 /* Checks every tensor arrived, builds fused/concatenated device layouts, captures the per-token CUDA graphs. */
 int xalm_cuda_finalize(xalm_cuda_model* m);
 void xalm_cuda_destroy(xalm_cuda_model* m);

@@ -164,3 +164,33 @@ def test_prefill_single_token_and_full_cache():
     with pytest.raises(capi.XalmError):
         gm.prefill(tokens[:2], config["max_seq_len"] - 1, want_logits=0)
     gm.close(); om.close()
+
+
+def test_prefill_4096_tokens_vs_oracle():
+    """BASELINE config 3 at its full length: 4096 positions in one pass through attn_tc_kernel (head_dim 128, GQA 8:2) and the
+    tcgen05 GEMMs, against the ORACLE run token by token (not against the repo's own decode kernels): logits at 40 positions
+    spread over the sequence plus the last 8, max-abs 1e-2, and Sampler::sample_prob at every position."""
+    config, om, gm = synth_pair("small", "q8_0", seed=3, std=0.03, n_layers=2, max_seq_len=4096)
+    assert config["max_seq_len"] == 4096 and config["head_dim"] == 128
+    n = 4096
+    toks = np.random.default_rng(17).integers(3, config["vocab_size"], size=n + 1).astype(np.int32)
+    check = sorted(set(list(range(0, n, 100)) + list(range(n - 8, n)) + [1, 127, 128, 129, 2047, 2048]))
+    want = {}
+    probs_o = np.zeros(n, np.float32)
+    for pos in range(n):
+        lg = om.forward(int(toks[pos]), pos, 1)
+        probs_o[pos] = oracle.sample_prob(lg, int(toks[pos + 1]))
+        if pos in check:
+            want[pos] = lg.copy()
+    lg_all, probs = gm.prefill(toks[:-1], 0, want_logits=2, targets=toks[1:])
+    worst = max(float(np.max(np.abs(lg_all[pos] - want[pos]))) for pos in check)
+    assert worst <= LOGIT_TOL, f"4096-token prefill logits differ from the oracle by {worst}"
+    assert np.max(np.abs(probs - probs_o)) <= 1e-3 * float(probs_o.max()) + 1e-6
+    ppl_g, ppl_o = float(np.exp(-np.mean(np.log(probs)))), float(np.exp(-np.mean(np.log(probs_o))))
+    assert abs(ppl_g - ppl_o) <= 1e-3 * ppl_o, (ppl_g, ppl_o)
+    # and decoding continues from the prefilled cache: ring is full at 4096, so this token wraps (sinks active)
+    st = InferenceState(config)
+    gm.forward(st, int(toks[n]), n, 1)
+    lg_o = om.forward(int(toks[n]), n, 1)
+    assert np.max(np.abs(st.logits() - lg_o)) <= LOGIT_TOL
+    gm.close(); om.close()

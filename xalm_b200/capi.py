@@ -46,6 +46,8 @@ SYMBOLS = {
     "xalm_cuda_type_info": (_i, [_i, C.POINTER(_i), C.POINTER(_i)]),
     "xalm_cuda_create": (_i, [C.POINTER(XalmConfig), _i, _i, _i, C.POINTER(_vp)]),
     "xalm_cuda_upload_tensor": (_i, [_vp, C.c_char_p, _i, C.POINTER(_i), _i, _vp, _sz]),
+    "xalm_cuda_host_alloc": (_vp, [_sz]),
+    "xalm_cuda_host_free": (None, [_vp]),
     "xalm_cuda_shard_range": (_i, [_vp, C.c_char_p, C.POINTER(_i)]),
     "xalm_cuda_upload_tensor_shard": (_i, [_vp, C.c_char_p, _i, C.POINTER(_i), _i, C.POINTER(_i), _vp, _sz]),
     "xalm_cuda_finalize": (_i, [_vp]),

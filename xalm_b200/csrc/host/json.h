@@ -21,6 +21,7 @@ struct Value {
 	double num = 0;
 	bool is_int = false;
 	long long inum = 0;
+	unsigned long long unum = 0; // the same digits read as unsigned (xxh3 hashes exceed LLONG_MAX half of the time)
 	std::string str;
 	std::vector<Value> arr;
 	Object obj;
@@ -153,7 +154,10 @@ class Parser {
 			v.kind = Value::Number;
 			v.num = std::strtod(t.c_str(), nullptr);
 			v.is_int = integral;
-			if (integral) v.inum = std::strtoll(t.c_str(), nullptr, 10);
+			if (integral) {
+				v.inum = std::strtoll(t.c_str(), nullptr, 10);
+				v.unum = t[0] == '-' ? (unsigned long long) v.inum : std::strtoull(t.c_str(), nullptr, 10);
+			}
 		}
 		return v;
 	}

@@ -49,7 +49,7 @@ double hbm_peak_gbs() {
 void run_completion(const std::string& checkpoint_path, const std::string& prompt, int context, int num_steps) {
 	auto model_data = Xalm::load(checkpoint_path);
 	std::cout << "loading model " << checkpoint_path << std::endl;
-	Model model = Model::from_xalm(model_data, context);
+	Model model = Model::from_xalm(model_data, context, /*defer_load=*/true); // weights go disk -> pinned -> device in model.cuda()
 	printf("Model active bytes(m): %zu\n", model.active_bytes(model.config.max_seq_len) / (1024 * 1024));
 	std::cout << "Using CUDA" << std::endl;
 	model.cuda();
@@ -105,7 +105,7 @@ void run_completion(const std::string& checkpoint_path, const std::string& promp
 
 void run_perplexity(const std::string& checkpoint_path, const std::string& prompt, int context) {
 	auto model_data = Xalm::load(checkpoint_path);
-	Model model = Model::from_xalm(model_data, context);
+	Model model = Model::from_xalm(model_data, context, /*defer_load=*/true); // weights go disk -> pinned -> device in model.cuda()
 	std::cout << "Model active bytes with full context window: " << model.active_bytes(model.config.max_seq_len) << std::endl;
 	std::cout << "Using CUDA" << std::endl;
 	model.cuda();
@@ -158,7 +158,7 @@ void run_perplexity(const std::string& checkpoint_path, const std::string& promp
 
 void run_passkey(const std::string& checkpoint_path, int context, int n_junk, int passkey_pos) {
 	auto model_data = Xalm::load(checkpoint_path);
-	Model model = Model::from_xalm(model_data, context);
+	Model model = Model::from_xalm(model_data, context, /*defer_load=*/true); // weights go disk -> pinned -> device in model.cuda()
 	std::cout << "Model active bytes with full context window: " << model.active_bytes(model.config.max_seq_len) << std::endl;
 	std::cout << "Using CUDA" << std::endl;
 	model.cuda();
@@ -198,6 +198,27 @@ void run_passkey(const std::string& checkpoint_path, int context, int n_junk, in
 	std::cout << std::endl;
 }
 
+// -m verify: read every tensor of the checkpoint once and check its xxh3_64 against the header (host only, no device needed).
+// With -t <type>: additionally re-encode every F32/F16/BF16 matrix with Tensor::convert_to and print "<name> <type> <bytes> <xxh3>"
+// (the call sites the reference has commented out at main.cpp:54-63).
+int run_verify(const std::string& checkpoint_path, const std::string& convert_type) {
+	auto data = Xalm::load(checkpoint_path);
+	if (!Xalm::hash_check_available()) std::cout << "warning: libxxhash not found, hashes are NOT checked" << std::endl;
+	size_t n = 0, bytes = 0, hashed = 0;
+	for (const auto& [name, ti] : data.tensors) {
+		Tensor t = data.load_tensor(name); // throws std::runtime_error on a hash mismatch
+		n++; bytes += t.size; hashed += ti.has_hash ? 1 : 0;
+		if (!convert_type.empty() && t.shape.size() == 2 && (t.type.id == XALM_F32 || t.type.id == XALM_F16 || t.type.id == XALM_BF16)) {
+			const Type target = Type::parse(convert_type);
+			if (target == t.type) continue;
+			const Tensor c = t.convert_to(target);
+			std::cout << name << " " << c.type.name() << " " << c.size << " " << Xalm::xxh3(c.bytes(), c.size) << std::endl;
+		}
+	}
+	std::cout << "verified " << n << " tensors (" << hashed << " with a hash), " << bytes << " bytes" << std::endl;
+	return 0;
+}
+
 bool is_prefix_of(const std::string& full, const std::string& s) { return !s.empty() && full.compare(0, s.size(), s) == 0; }
 
 } // namespace
@@ -206,6 +227,7 @@ int main(int argc, char* argv[]) {
 	std::string checkpoint_path, device = "cuda", mode = "completion";
 	std::string prompt = "Q: What is the meaning of life? A:"; // main.cpp:421
 	std::string prompt_path;
+	std::string convert_type;
 	int context = 0, num_steps = 128, n_junk = 250, passkey_pos = -1;
 	if (argc >= 2) checkpoint_path = argv[1];
 	else error_usage();
@@ -217,6 +239,7 @@ int main(int argc, char* argv[]) {
 			if (is_prefix_of("completion", v)) mode = "completion";
 			else if (is_prefix_of("passkey", v)) mode = "passkey";
 			else if (is_prefix_of("perplexity", v)) mode = "perplexity";
+			else if (is_prefix_of("verify", v)) mode = "verify";
 			else error_usage();
 		} else if (f == 'd') {
 			if (is_prefix_of("cpu", v)) device = "cpu";
@@ -225,10 +248,19 @@ int main(int argc, char* argv[]) {
 		} else if (f == 'i') prompt = v;
 		else if (f == 'f') prompt_path = v;
 		else if (f == 'T') context = std::stoi(v);
+		else if (f == 't') convert_type = v;
 		else if (f == 'l') passkey_pos = std::stoi(v);
 		else if (f == 'n') { num_steps = std::stoi(v); n_junk = num_steps; }
 		else error_usage();
 		i += 2;
+	}
+	if (mode == "verify") {
+		try {
+			return run_verify(checkpoint_path, convert_type);
+		} catch (const std::exception& e) {
+			fprintf(stderr, "error: %s\n", e.what());
+			return 1;
+		}
 	}
 	if (device != "cuda") {
 		fprintf(stderr, "Error: this binary is the CUDA backend; it carries no CPU forward pass (use the reference for -d cpu)\n");

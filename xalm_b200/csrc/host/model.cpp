@@ -1,6 +1,10 @@
 // model.cpp — host-side implementation of the reference surface declared in model.h, over the C ABI.
 #include "model.h"
 
+#include <dlfcn.h>
+#include <fcntl.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <cctype>
 #include <cmath>
@@ -69,6 +73,31 @@ Tensor Tensor::zeroes(Type type, const std::vector<int>& shape, const std::strin
 	return t;
 }
 
+Tensor Tensor::convert_to(const Type target_type) const {
+	if (!data_) throw std::invalid_argument("Tensor data cannot be null");
+	if (type == target_type) throw std::invalid_argument("Tensor is already of target dtype."); // the reference prints this and exits
+	if (type.id != XALM_F32 && type.id != XALM_F16 && type.id != XALM_BF16)
+		throw std::invalid_argument(std::string("Unsupported conversion from dtype: ") + std::string(type.name()));
+	const size_t cols = shape.empty() ? 1 : (size_t) shape.back();
+	if (cols % (size_t) target_type.block) throw std::invalid_argument("row length is not a multiple of the target block size");
+	std::vector<float> f(linear_length);
+	if (type.id == XALM_F32) std::memcpy(f.data(), data_.get(), linear_length * 4);
+	else if (type.id == XALM_F16) {
+		const _Float16* h = reinterpret_cast<const _Float16*>(data_.get());
+		for (size_t i = 0; i < linear_length; i++) f[i] = (float) h[i];
+	} else {
+		const uint16_t* b = reinterpret_cast<const uint16_t*>(data_.get());
+		for (size_t i = 0; i < linear_length; i++) {
+			const uint32_t u = (uint32_t) b[i] << 16; // types.h:322-325
+			std::memcpy(&f[i], &u, 4);
+		}
+	}
+	Tensor out = Tensor::zeroes(target_type, shape, name);
+	if (xalm_host_quantize(target_type.id, f.data(), (long long) (linear_length / cols), (long long) cols, out.bytes()) != 0)
+		throw std::invalid_argument(std::string("Unsupported conversion to dtype: ") + std::string(target_type.name()));
+	return out;
+}
+
 // ---- Xalm::load (xalm.h:90-192) --------------------------------------------------------------------------------
 static std::string expand_tilde(const std::string& path) {
 	if (path.empty() || path[0] != '~') return path;
@@ -128,6 +157,10 @@ Xalm::file_info Xalm::load(const std::string& file_name_in) {
 				throw std::invalid_argument("offset out of range");
 			ti.offset = header_end + (size_t) off->inum;
 			ti.size = (size_t) sz->inum;
+			if (const xjson::Value* hv = tv.find("hash"); hv && hv->kind == xjson::Value::Number && hv->is_int) {
+				ti.hash = hv->unum; // xxh3_64 of the payload (convert.py:265-266)
+				ti.has_hash = true;
+			}
 			size_t n = 1;
 			for (int d : ti.shape) n *= (size_t) d;
 			if (n % (size_t) ti.type.block || ti.type.nbytes(n) != ti.size)
@@ -140,12 +173,47 @@ Xalm::file_info Xalm::load(const std::string& file_name_in) {
 	return fi;
 }
 
+// XXH3_64bits from the system's libxxhash (0.8.x, the library convert.py's `xxhash` module wraps), resolved at run time so the
+// host library has no link-time dependency on it; nullptr when the box has none (the check is then skipped, as the reference
+// always does: xalm.h:90-192 parses "hash" and never looks at it).
+using xxh3_fn = unsigned long long (*)(const void*, size_t);
+static xxh3_fn xxh3_64bits() {
+	static xxh3_fn fn = []() -> xxh3_fn {
+		if (std::getenv("XALM_NO_HASH_CHECK")) return nullptr;
+		for (const char* lib : {"libxxhash.so.0", "libxxhash.so"})
+			if (void* h = dlopen(lib, RTLD_NOW | RTLD_LOCAL))
+				if (void* f = dlsym(h, "XXH3_64bits")) return reinterpret_cast<xxh3_fn>(f);
+		return nullptr;
+	}();
+	return fn;
+}
+bool Xalm::hash_check_available() { return xxh3_64bits() != nullptr; }
+unsigned long long Xalm::xxh3(const void* p, size_t n) { const xxh3_fn h = xxh3_64bits(); return h ? h(p, n) : 0ull; }
+
+Xalm::file_info::~file_info() {
+	if (fd_ >= 0) ::close(fd_);
+}
+
+// One descriptor per checkpoint, positional reads: no reopen + seek per tensor (model.cpp:57 constructs an ifstream per tensor).
 void Xalm::file_info::load_tensor_data(const tensor_info& ti, uint8_t* dst, size_t n) const {
 	if (n != ti.size) throw std::runtime_error("buffer size mismatch"); // xalm.h:27-29
-	std::ifstream stream(ti.file_name, std::ios::binary);
-	stream.seekg((std::streamoff) ti.offset, std::ios::beg);
-	stream.read(reinterpret_cast<char*>(dst), (std::streamsize) n);
-	if ((size_t) stream.gcount() != n) throw std::runtime_error("short read for tensor " + ti.name);
+	if (fd_ < 0) {
+		fd_ = ::open(ti.file_name.c_str(), O_RDONLY);
+		if (fd_ < 0) throw std::runtime_error("cannot open " + ti.file_name);
+	}
+	size_t done = 0;
+	while (done < n) {
+		const ssize_t r = ::pread(fd_, dst + done, n - done, (off_t) (ti.offset + done));
+		if (r <= 0) throw std::runtime_error("short read for tensor " + ti.name);
+		done += (size_t) r;
+	}
+	if (ti.has_hash) {
+		if (const xxh3_fn h = xxh3_64bits()) {
+			const unsigned long long got = h(dst, n);
+			if (got != ti.hash)
+				throw std::runtime_error("hash mismatch for tensor " + ti.name + ": header " + std::to_string(ti.hash) + ", payload " + std::to_string(got));
+		}
+	}
 }
 
 Tensor Xalm::file_info::load_tensor(const std::string& name) const {
@@ -209,7 +277,7 @@ Model::~Model() {
 }
 
 // Model::from_xalm (model.cpp:48-118): same tensor names, same expected shapes, same failure modes
-Model Model::from_xalm(Xalm::file_info& xalm, const int context) {
+Model Model::from_xalm(Xalm::file_info& xalm, const int context, const bool defer_load) {
 	const Config config = Config::from_xalm(xalm, context);
 	Model m(config);
 	auto load = [&](const std::string& name, const std::vector<int>& expected) {
@@ -225,8 +293,9 @@ Model Model::from_xalm(Xalm::file_info& xalm, const int context) {
 			throw std::invalid_argument("shape mismatch for " + name + ": " + fmt(ti.shape) + " vs " + fmt(expected) + " expected!");
 		}
 		m.types_[name] = ti.type;
-		m.host_.emplace(name, xalm.load_tensor(name));
+		if (!defer_load) m.host_.emplace(name, xalm.load_tensor(name));
 	};
+	if (defer_load) m.deferred_ = &xalm;
 	const int q_dim = config.n_heads * config.head_dim, kv_dim = config.n_kv_heads * config.head_dim;
 	load("embed.weight", {config.vocab_size, config.dim});
 	for (int i = 0; i < config.n_layers; ++i) {
@@ -254,6 +323,37 @@ void Model::cuda(int device_index, int tp_rank, int tp_size, const void* comm_id
 	if (tp_size > 1) {
 		if (!comm_id) throw std::invalid_argument("model.cuda(): tensor parallel needs a communicator id");
 		if (xalm_cuda_comm_init(handle_, comm_id) != XALM_OK) xalm_throw_last("model.cuda()");
+	}
+	if (deferred_) {
+		// disk -> pinned staging -> device, one tensor at a time; row-sharded tensors read only this rank's rows
+		size_t cap = 0;
+		for (const auto& [name, ty] : types_) cap = std::max(cap, deferred_->tensors.at(name).size);
+		uint8_t* stage = static_cast<uint8_t*>(xalm_cuda_host_alloc(cap));
+		if (!stage) xalm_throw_last("model.cuda()");
+		struct Guard { uint8_t* p; ~Guard() { xalm_cuda_host_free(p); } } guard{stage};
+		for (const auto& [name, ty] : types_) {
+			const Xalm::tensor_info& ti = deferred_->tensors.at(name);
+			int rng[4];
+			if (xalm_cuda_shard_range(handle_, name.c_str(), rng) != XALM_OK) xalm_throw_last("model.cuda()");
+			const int rows = ti.shape.empty() ? 1 : ti.shape[0];
+			const int cols = ti.shape.size() > 1 ? ti.shape[1] : 1;
+			const bool row_shard = ti.shape.size() == 2 && rng[2] == 0 && rng[3] == cols && (rng[0] != 0 || rng[1] != rows);
+			int rc;
+			if (row_shard) { // a contiguous byte range of the payload (the header's hash covers the whole tensor: not checked here)
+				const size_t row_bytes = ti.type.nbytes((size_t) cols);
+				Xalm::tensor_info part = ti;
+				part.offset = ti.offset + (size_t) rng[0] * row_bytes;
+				part.size = (size_t) (rng[1] - rng[0]) * row_bytes;
+				part.has_hash = false;
+				deferred_->load_tensor_data(part, stage, part.size);
+				rc = xalm_cuda_upload_tensor_shard(handle_, name.c_str(), ti.type.id, ti.shape.data(), (int) ti.shape.size(), rng, stage, part.size);
+			} else { // replicated or column-split: the whole tensor (hash verified), the backend keeps its columns
+				deferred_->load_tensor_data(ti, stage, ti.size);
+				rc = xalm_cuda_upload_tensor(handle_, name.c_str(), ti.type.id, ti.shape.data(), (int) ti.shape.size(), stage, ti.size);
+			}
+			if (rc != XALM_OK) xalm_throw_last("model.cuda()");
+		}
+		deferred_ = nullptr;
 	}
 	for (auto it = host_.begin(); it != host_.end();) {
 		const Tensor& t = it->second;

@@ -53,6 +53,10 @@ public:
 	size_t linear_length = 0; // elements
 
 	static Tensor zeroes(Type type, const std::vector<int>& shape, const std::string& name = "");
+	// Tensor::convert_to (tensor.cpp:226-296), extended to the block formats the reference only defines in Python: an F32 / F16 /
+	// BF16 tensor re-encoded as F32, F16, BF16, Q8 or Q8_0 / Q4_0 / Q4_1 / Q5_0 / Q5_1 / TQ1_0 with quants.py's quantiser rules
+	// (byte-identical to quants.py, tests/test_quantize.py).  Throws std::invalid_argument for a pair it does not take.
+	[[nodiscard]] Tensor convert_to(Type target_type) const;
 	template <typename T>
 	const T* get_data() const { return reinterpret_cast<const T*>(data_.get()); }
 	uint8_t* bytes() { return data_.get(); }
@@ -82,9 +86,19 @@ struct Xalm {
 		std::map<std::string, std::string> metadata; // the "config" object: every value is a string
 		std::map<std::string, tensor_info> tensors;
 		Tensor load_tensor(const std::string& name) const;
+		// reads the payload (one descriptor per file, pread) and verifies its xxh3_64 against the header's "hash" when present
 		void load_tensor_data(const tensor_info& ti, uint8_t* dst, size_t n) const;
+		file_info() = default;
+		file_info(file_info&& o) noexcept : file_name(std::move(o.file_name)), arch(std::move(o.arch)), metadata(std::move(o.metadata)),
+		                                    tensors(std::move(o.tensors)), fd_(o.fd_) { o.fd_ = -1; }
+		file_info(const file_info&) = delete;
+		~file_info();
+	private:
+		mutable int fd_ = -1;
 	};
 	static file_info load(const std::string& file_name);
+	static bool hash_check_available(); // libxxhash found on this box
+	static unsigned long long xxh3(const void* p, size_t n); // XXH3_64bits (0 when the library is missing)
 };
 
 // ---- Config (model.h:25-91) -------------------------------------------------------------------------------------
@@ -124,7 +138,10 @@ enum class InferenceMode { HYDRATE_KV_CACHE, OUTPUT_LOGITS };
 
 // ---- Model (model.h:254-284) ------------------------------------------------------------------------------------
 struct Model {
-	static Model from_xalm(Xalm::file_info& xalm, int context);
+	// defer_load: do not read the weights into host memory now — model.cuda() then streams each tensor disk -> pinned staging
+	// buffer -> device, and a tensor-parallel rank reads only the rows it keeps (the reference reads everything whole first,
+	// model.cpp:48-118).  The file_info must outlive the cuda() call.
+	static Model from_xalm(Xalm::file_info& xalm, int context, bool defer_load = false);
 	Model(Model&&) noexcept;
 	Model(const Model&) = delete;
 	Model& operator=(const Model&) = delete;
@@ -148,6 +165,7 @@ private:
 	explicit Model(const Config& c) : config(c) {}
 	std::map<std::string, Tensor> host_; // until cuda()
 	std::map<std::string, Type> types_;  // kept for active_bytes after the host copies are gone
+	const Xalm::file_info* deferred_ = nullptr; // defer_load: where cuda() reads the tensors from
 	xalm_cuda_model* handle_ = nullptr;
 	int tp_size_ = 1;
 };

@@ -1069,6 +1069,16 @@ static int expected_shape(const xalm_cuda_model* m, int piece, int* er, int* ec,
 	return XALM_OK;
 }
 
+void* xalm_cuda_host_alloc(size_t nbytes) {
+	void* p = nullptr;
+	cudaError_t e = cudaMallocHost(&p, nbytes ? nbytes : 16);
+	if (e != cudaSuccess) { set_error(XALM_ERR_CUDA, "cudaMallocHost(%zu) failed: %s", nbytes, cudaGetErrorString(e)); return nullptr; }
+	return p;
+}
+void xalm_cuda_host_free(void* p) {
+	if (p) cudaFreeHost(p);
+}
+
 int xalm_cuda_shard_range(xalm_cuda_model* m, const char* name, int* range4) {
 	if (!m || !name || !range4) return set_error(XALM_ERR_INVALID, "NULL argument");
 	int layer, piece, er, ec;
