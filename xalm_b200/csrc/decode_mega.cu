@@ -382,7 +382,7 @@ __device__ __noinline__ unsigned int dm_attention(const DmPhase& P, const StepPa
 		if (tls) tls[6] = gtime();
 		dm_signal(ctr);
 		expected += gridDim.x;
-		if ((int) blockIdx.x * 32 < n_out) dm_wait(ctr, expected, ab);
+		dm_wait(ctr, expected, ab); // EVERY CTA: one that ran ahead to its end-of-phase signal would be counted in place of a late split
 		if (tls) tls[7] = gtime();
 		float* s_ms = scratch;                    // [DM_MAX_SPLITS] split maxima of this head
 		float* s_num = scratch + DM_MAX_SPLITS;   // [8][32]

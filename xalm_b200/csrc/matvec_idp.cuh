@@ -18,12 +18,16 @@
 namespace xalm {
 
 constexpr int IDP_KW = 4, IDP_RW = 2, IDP_R = 4, IDP_RC = IDP_RW * IDP_R, IDP_U = 16;
+// Partial sums of the K-slice warps are handed to the tile's reducer warp through IDP_PB buffers, each with an mbarrier the 8 consumer
+// warps arrive on: nobody but the reducer ever waits (a CTA-wide bar.sync per tile was 26 % of all stall cycles, profiles/r2_idp_ncu.md).
+// A buffer is reused IDP_PB tiles later; a warp cannot be more than NS (<= 5) tiles ahead of the reducer's own compute (ring), so 8 is safe.
+constexpr int IDP_PB = 8;
 
 __host__ __device__ inline size_t idp_smem_bytes(int type, int n, int NS) {
 	size_t s = (xq_bytes(n) + 127) / 128 * 128;
 	s += (size_t) NS * IDP_RC * IDP_U * unit_bytes(type);
-	s += 2 * IDP_KW * IDP_RC * sizeof(float);   // partials, double-buffered
-	s += 2 * (size_t) NS * sizeof(uint64_t);    // full / empty barriers
+	s += IDP_PB * IDP_KW * IDP_RC * sizeof(float); // partials, IDP_PB tiles deep
+	s += (2 * (size_t) NS + IDP_PB) * sizeof(uint64_t); // full / empty / partial barriers
 	s += 16 * sizeof(float);                    // reduction scratch
 	return s + 128;
 }
@@ -50,9 +54,10 @@ __global__ void __maxnreg__(96) matvec_idp_kernel(const IdpArgs ta) {
 	uint8_t* xq_base = smem;
 	uint8_t* ring = smem + (xq_bytes(n) + 127) / 128 * 128;
 	float* part = reinterpret_cast<float*>(ring + (size_t) NS * SLOT);
-	float* s_red = part + 2 * KW * RC;
+	float* s_red = part + IDP_PB * KW * RC;
 	uint64_t* full = reinterpret_cast<uint64_t*>(s_red + 16);
 	uint64_t* empty = full + NS;
+	uint64_t* pbar = empty + NS;
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	if (threadIdx.x == 0) {
@@ -60,6 +65,7 @@ __global__ void __maxnreg__(96) matvec_idp_kernel(const IdpArgs ta) {
 			mbar_init(&full[s], 1);
 			mbar_init(&empty[s], TMA_NW);
 		}
+		for (int s = 0; s < IDP_PB; s++) mbar_init(&pbar[s], TMA_NW);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
@@ -274,11 +280,13 @@ __global__ void __maxnreg__(96) matvec_idp_kernel(const IdpArgs ta) {
 			k += __shfl_xor_sync(0xffffffffu, k, 4);
 			k += __shfl_xor_sync(0xffffffffu, k, 2);
 			k += __shfl_xor_sync(0xffffffffu, k, 1);
-			if ((lane & 7) == 0) part[(tt & 1) * (KW * RC) + kw * RC + rw * R + (b4 ? 2 : 0) + (b3 ? 1 : 0)] = k;
+			if ((lane & 7) == 0) part[(tt % IDP_PB) * (KW * RC) + kw * RC + rw * R + (b4 ? 2 : 0) + (b3 ? 1 : 0)] = k;
 		}
-		consumer_bar_sync();
+		__syncwarp();
+		if (lane == 0) mbar_arrive(&pbar[tt % IDP_PB]); // (release: this warp's partial sums are visible to whoever completes the wait)
 		if (reducer) { // rotating reducer: lane i owns row i of the tile
-			const float* pt = part + (tt & 1) * (KW * RC);
+			mbar_wait(&pbar[tt % IDP_PB], (tt / IDP_PB) & 1);
+			const float* pt = part + (tt % IDP_PB) * (KW * RC);
 			float yv = 0.f;
 			if (lane < RC) {
 #pragma unroll
