@@ -11,7 +11,7 @@
 // where the activation block is held as block floating point — one power-of-two scale dx per 32 elements and three
 // int8 limbs per element (X = 65536*l0 + 256*l1 + l2; l0 signed, l1, l2 unsigned), so one IDP.4A handles four weights
 // against one limb: 24 dp4a per 32-weight block instead of 64-136 PRMT/FADD2/FFMA2.  The integer sums are exact; the
-// only rounding beyond the reference's is x -> 23 bits + sign relative to its block maximum (<= 2^-24 of the largest
+// only rounding beyond the reference's is x -> 23 bits + sign relative to its block maximum (<= 2^-23 of the largest
 // |x| of the block — measured against fp64 the result is CLOSER than sequential fp32 accumulation, tests/test_idp_cpu.py).
 // With a one-hot x the arithmetic is exact and returns the dequantised weight bit for bit (d*q is exact in fp32,
 // d*q+m rounds once, as in quants.py).
