@@ -536,27 +536,36 @@ def main():
         prompt = [1] + [int(t) for t in np.random.default_rng(7).integers(3, cfg["vocab_size"], size=3)]
         pstate = InferenceState(cfg).cuda()
         psampler = Sampler(cfg)
+        # The GPU ranks decode first, in lock step (a rank that stopped to run the CPU oracle between tokens would leave its peers
+        # spinning in the tensor-parallel exchange until their timeout); rank 0 keeps every step's logits and replays the oracle after.
+        if world > 1:
+            dist.barrier()
+        for p_, t_ in enumerate(prompt):
+            model.forward(pstate, t_, p_, 1 if p_ + 1 == len(prompt) else 0)
+        seq_g, lg_g = list(prompt), []
+        for _ in range(args.parity_tokens):
+            tg = psampler.sample_argmax(pstate)
+            if rank == 0:
+                lg_g.append(np.array(pstate.logits(), dtype=np.float32, copy=True))
+            seq_g.append(tg)
+            model.forward(pstate, tg, len(seq_g) - 1, 1)
         om = None
         if rank == 0:
             from oracle import oracle
             oracle.set_threads(max(1, (os.cpu_count() or 1)))
             om = oracle.OracleModel(cfg, host_tensors, acc_mode=1)
-        lg_o = None
-        for p_, t_ in enumerate(prompt):
-            last = p_ + 1 == len(prompt)
-            model.forward(pstate, t_, p_, 1 if last else 0)
-            if om:
-                lg_o = om.forward(t_, p_, 1 if last else 0)
-        seq_g, seq_o, worst = list(prompt), list(prompt), 0.0
-        for _ in range(args.parity_tokens):
-            tg = psampler.sample_argmax(pstate)
-            if om:
-                worst = max(worst, float(np.max(np.abs(pstate.logits() - lg_o))))
+            lg_o = None
+            for p_, t_ in enumerate(prompt):
+                lg_o = om.forward(t_, p_, 1 if p_ + 1 == len(prompt) else 0)
+            seq_o, worst = list(prompt), 0.0
+            for i in range(args.parity_tokens):
+                if seq_o == seq_g[: len(seq_o)]:      # same history so far: the logits are comparable
+                    worst = max(worst, float(np.max(np.abs(lg_g[i] - lg_o))))
                 to = oracle.sample_argmax(lg_o)
                 seq_o.append(to)
-                lg_o = om.forward(to, len(seq_o) - 1, 1)
-            seq_g.append(tg)
-            model.forward(pstate, tg, len(seq_g) - 1, 1)
+                if i + 1 < args.parity_tokens:
+                    lg_o = om.forward(to, len(seq_o) - 1, 1)
+            seq_g = seq_g[: len(seq_o)]
         if om:
             om.close()
             parity = {"tokens_match": seq_g == seq_o, "max_abs_logit": worst, "tolerance": 1e-2, "greedy_tokens": args.parity_tokens,
@@ -630,6 +639,8 @@ def main():
                                 "sample": f"{n} tokens at positions spread uniformly over [0, {ctx}) of the same model (full depth, same weights), wall clock"}
     if rank == 0:
         print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()      # peers keep their exchange buffers mapped until rank 0 is through with the oracle replay
     model.close()
     if world > 1:
         dist.destroy_process_group()
