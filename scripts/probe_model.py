@@ -54,14 +54,19 @@ for kn in configs:
         order = np.argsort(tl[:, 1])
         prev_end = None
         rows = []
-        for i in order[: 5 * 4 + 3]:
+        for i in order[: int(os.environ.get('TL_ROWS', 5 * 4 + 3))]:
             kid, a, b, c = tl[i]
+            if kid >= 500:
+                rows.append(f"      event {int(kid)} at {(a-t0)/1e3:8.2f}us")
+                continue
             rows.append(f"  {str(names.get(int(kid), kid)):10s} entry {(a-t0)/1e3:8.2f}us  wait_done {(b-t0)/1e3:8.2f}  exit {(c-t0)/1e3:8.2f}  | entry->wait {(b-a)/1e3:6.2f}  work {(c-b)/1e3:6.2f}" + (f"  gap_from_prev_exit {(b-prev_end)/1e3:6.2f}" if prev_end else ""))
             prev_end = c
         print("\n".join(rows))
         tot = (tl[:, 3].max() - t0) / 1e3
         work = {}
         for kid, a, b, c in tl:
+            if kid >= 500:
+                continue
             work.setdefault(names.get(int(kid), kid), []).append((c - b) / 1e3)
         print(f"  token total {tot:.1f}us;", {k: (len(v), round(float(np.mean(v)), 2)) for k, v in work.items()})
     model.close()

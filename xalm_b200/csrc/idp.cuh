@@ -71,6 +71,48 @@ __device__ __forceinline__ void xq_store_block(const XqView& v, int blk, const f
 	v.meta[blk] = make_int4(s0, s1, s2, (int) __float_as_uint(dx));
 }
 
+// The staging used by the kernels: EIGHT consecutive elements per lane, the four lanes 4k..4k+3 of a warp share a block (call with
+// all lanes of the warp).  Loads are coalesced (32 bytes per lane, 1 KB per warp instruction) and every thread of the CTA works;
+// the thread-per-block version above left half the CTA idle behind 32 line-strided loads per lane and took 7 us of a 25 us
+// kernel (profiles/r2_decode_timeline.md).  Same image in shared memory, bit for bit.
+__device__ __forceinline__ void xq_store_group8(const XqView& v, int grp, const float (&x)[8]) {
+	uint32_t mb = 0;
+#pragma unroll
+	for (int e = 0; e < 8; e++) mb = max(mb, __float_as_uint(x[e]) & 0x7fffffffu);
+	mb = max(mb, __shfl_xor_sync(0xffffffffu, mb, 1));
+	mb = max(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
+	const int eb = (int) (mb >> 23);
+	const bool live = eb >= 40 && eb < 255;
+	const float sc = live ? __uint_as_float((uint32_t) (276 - eb) << 23) : 0.f;
+	const float dx = live ? __uint_as_float((uint32_t) (eb - 22) << 23) : 0.f;
+	uint32_t w[3][2];
+	int s0 = 0;
+	uint32_t s1 = 0, s2 = 0;
+#pragma unroll
+	for (int q = 0; q < 2; q++) {
+		int X[4];
+#pragma unroll
+		for (int e = 0; e < 4; e++) X[e] = min(__float2int_rn(x[4 * q + e] * sc), 8388607);
+#pragma unroll
+		for (int k = 0; k < 3; k++) {
+			const uint32_t sel = (uint32_t) k | ((uint32_t) (4 + k) << 4);
+			const uint32_t lo = prmt((uint32_t) X[0], (uint32_t) X[1], sel), hi = prmt((uint32_t) X[2], (uint32_t) X[3], sel);
+			w[2 - k][q] = prmt(lo, hi, 0x5410u);
+		}
+		asm("dp4a.s32.u32 %0, %1, %2, %0;" : "+r"(s0) : "r"(w[0][q]), "r"(0x01010101u));
+		asm("dp4a.u32.u32 %0, %1, %2, %0;" : "+r"(s1) : "r"(w[1][q]), "r"(0x01010101u));
+		asm("dp4a.u32.u32 %0, %1, %2, %0;" : "+r"(s2) : "r"(w[2][q]), "r"(0x01010101u));
+	}
+	uint32_t u = s1 | (s2 << 16); // block totals <= 32 * 255 < 2^16 each: one shuffle pair reduces both
+	u += __shfl_xor_sync(0xffffffffu, u, 1);
+	u += __shfl_xor_sync(0xffffffffu, u, 2);
+	s0 += __shfl_xor_sync(0xffffffffu, s0, 1);
+	s0 += __shfl_xor_sync(0xffffffffu, s0, 2);
+#pragma unroll
+	for (int k = 0; k < 3; k++) *reinterpret_cast<uint2*>(v.q + (size_t) k * v.n + (size_t) grp * 8) = make_uint2(w[k][0], w[k][1]);
+	if ((grp & 3) == 0) v.meta[grp >> 2] = make_int4(s0, (int) (u & 0xFFFFu), (int) (u >> 16), (int) __float_as_uint(dx));
+}
+
 // what one lane holds of an activation block while it walks the R rows of a tile
 struct XqBlock {
 	uint4 a[3];   // limb k, the 16 elements of half hA of the block

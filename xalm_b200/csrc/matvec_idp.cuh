@@ -22,6 +22,7 @@ constexpr int IDP_KW = 4, IDP_RW = 2, IDP_R = 4, IDP_RC = IDP_RW * IDP_R, IDP_U 
 // warps arrive on: nobody but the reducer ever waits (a CTA-wide bar.sync per tile was 26 % of all stall cycles, profiles/r2_idp_ncu.md).
 // A buffer is reused IDP_PB tiles later; a warp cannot be more than NS (<= 5) tiles ahead of the reducer's own compute (ring), so 8 is safe.
 constexpr int IDP_PB = 8;
+constexpr int IDP_MP = 4; // staging passes of a norm-fused kernel: 8 elements x 256 lanes x 4 = n <= 8192
 
 __host__ __device__ inline size_t idp_smem_bytes(int type, int n, int NS) {
 	size_t s = (xq_bytes(n) + 127) / 128 * 128;
@@ -120,16 +121,23 @@ __global__ void __maxnreg__(96) matvec_idp_kernel(const IdpArgs ta) {
 	}
 
 	// ===================== consumers =====================
-	// Staging: thread t owns 32-element block t (+256, ...).  The rmsnorm weights of that block do not depend on the previous
-	// kernel: request them before the dependency wait (host: NORM only with n <= 8192, one block per thread).
+	// Staging: lane t of the CTA owns the 8-element groups t, t + 256, ... (four lanes per 32-element block).  The rmsnorm weights do
+	// not depend on the previous kernel: request them before the dependency wait (host: NORM only with n <= 8192 = IDP_MP passes).
 	const int tid = threadIdx.x;
-	uint4 gw[NORM ? 4 : 1]; // BF16 weights travel packed (16 registers); F32 ones are pulled into L2 now and read after the reduction
-	if (NORM && tid < nb_row) {
-		if (a.norm_type == XALM_F32) {
-			asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const float*>(a.norm_w) + tid * 32));
-		} else {
+	const int ngrp = n / 8;
+	uint4 gw[NORM ? IDP_MP : 1][2];
+	if (NORM) {
 #pragma unroll
-			for (int c = 0; c < 4; c++) gw[c] = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.norm_w) + tid * 32 + 8 * c);
+		for (int p = 0; p < IDP_MP; p++) {
+			const int grp = p * (TMA_NW * 32) + tid;
+			if (grp < ngrp) {
+				if (a.norm_type == XALM_F32) {
+					gw[p][0] = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(a.norm_w) + grp * 8);
+					gw[p][1] = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(a.norm_w) + grp * 8 + 4);
+				} else {
+					gw[p][0] = *reinterpret_cast<const uint4*>(reinterpret_cast<const uint16_t*>(a.norm_w) + grp * 8);
+				}
+			}
 		}
 	}
 	pdl_wait(); // activations / KV ring of earlier kernels are visible from here on
@@ -176,12 +184,12 @@ __global__ void __maxnreg__(96) matvec_idp_kernel(const IdpArgs ta) {
 	// ---- stage activations: xq = quantise(NORM ? x * scale * g : x) ----
 	const XqView xv = xq_view(xq_base, n);
 	{
-		auto load_block = [&](int blk, float (&v)[32]) {
+		auto load_group = [&](int grp, float (&v)[8]) {
 			if (NORM && a.n_recv) { // the summed stream, published by the reducing CTAs as {value, tag} words: poll this exchange's tag
 				const unsigned int seq = a.step->ar_base + (unsigned int) a.recv_idx + 1u;
 #pragma unroll
-				for (int c = 0; c < 8; c++) {
-					const uint2* src = a.xl + blk * 32 + 4 * c;
+				for (int c = 0; c < 2; c++) {
+					const uint2* src = a.xl + grp * 8 + 4 * c;
 					uint4 w0, w1;
 					unsigned int spins = 0;
 					do {
@@ -192,20 +200,26 @@ __global__ void __maxnreg__(96) matvec_idp_kernel(const IdpArgs ta) {
 					v[4 * c] = __uint_as_float(w0.x); v[4 * c + 1] = __uint_as_float(w0.z); v[4 * c + 2] = __uint_as_float(w1.x); v[4 * c + 3] = __uint_as_float(w1.z);
 				}
 			} else {
-#pragma unroll
-				for (int c = 0; c < 8; c++) {
-					const float4 q = ld_act4(a.x + blk * 32 + 4 * c);
-					v[4 * c] = q.x; v[4 * c + 1] = q.y; v[4 * c + 2] = q.z; v[4 * c + 3] = q.w;
-				}
+				const float4 q0 = ld_act4(a.x + grp * 8), q1 = ld_act4(a.x + grp * 8 + 4);
+				v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w;
+				v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
 			}
 		};
 		if (NORM) {
-			float xr[32];
+			float xr[IDP_MP][8];
 			float ss = 0.f;
-			if (tid < nb_row) {
-				load_block(tid, xr);
 #pragma unroll
-				for (int e = 0; e < 32; e++) ss += xr[e] * xr[e];
+			for (int p = 0; p < IDP_MP; p++) {
+				const int grp = p * (TMA_NW * 32) + tid;
+				if (grp < ngrp) load_group(grp, xr[p]);
+			}
+#pragma unroll
+			for (int p = 0; p < IDP_MP; p++) {
+				const int grp = p * (TMA_NW * 32) + tid;
+				if (grp < ngrp) {
+#pragma unroll
+					for (int e = 0; e < 8; e++) ss += xr[p][e] * xr[p][e];
+				}
 			}
 			ss = warp_sum(ss);
 			if (lane == 0) s_red[warp] = ss;
@@ -214,31 +228,46 @@ __global__ void __maxnreg__(96) matvec_idp_kernel(const IdpArgs ta) {
 #pragma unroll
 			for (int i = 0; i < TMA_NW; i++) tot += s_red[i];
 			const float scale = 1.0f / sqrtf(tot / (float) n + a.norm_eps);
-			if (tid < nb_row) {
 #pragma unroll
-				for (int e = 0; e < 32; e++) {
-					float g;
-					if (a.norm_type == XALM_F32) {
-						g = reinterpret_cast<const float*>(a.norm_w)[tid * 32 + e];
-					} else {
-						const uint4 q = gw[e >> 3];
-						const int h = (e & 7) >> 1;
-						const uint32_t u = h == 0 ? q.x : h == 1 ? q.y : h == 2 ? q.z : q.w;
-						g = __uint_as_float((e & 1) ? (u & 0xFFFF0000u) : (u << 16));
+			for (int p = 0; p < IDP_MP; p++) {
+				const int grp = p * (TMA_NW * 32) + tid;
+				if (grp < ngrp) { // (warp-uniform: n % 256 == 0)
+#pragma unroll
+					for (int e = 0; e < 8; e++) {
+						float g;
+						if (a.norm_type == XALM_F32) {
+							const uint4 q = gw[p][e >> 2];
+							g = __uint_as_float((e & 3) == 0 ? q.x : (e & 3) == 1 ? q.y : (e & 3) == 2 ? q.z : q.w);
+						} else {
+							const uint4 q = gw[p][0];
+							const int h = e >> 1;
+							const uint32_t u = h == 0 ? q.x : h == 1 ? q.y : h == 2 ? q.z : q.w;
+							g = __uint_as_float((e & 1) ? (u & 0xFFFF0000u) : (u << 16));
+						}
+						xr[p][e] = xr[p][e] * scale * g; // infer.cpp:233-235
 					}
-					xr[e] = xr[e] * scale * g; // infer.cpp:233-235
+					xq_store_group8(xv, grp, xr[p]);
 				}
-				xq_store_block(xv, tid, xr);
 			}
 		} else {
-			for (int blk = tid; blk < nb_row; blk += TMA_NW * 32) {
-				float xr[32];
-				load_block(blk, xr);
-				xq_store_block(xv, blk, xr);
+			constexpr int UNR = 4; // groups in flight per lane
+			for (int base = 0; base < ngrp; base += UNR * TMA_NW * 32) {
+				float xr[UNR][8];
+#pragma unroll
+				for (int p = 0; p < UNR; p++) {
+					const int grp = base + p * (TMA_NW * 32) + tid;
+					if (grp < ngrp) load_group(grp, xr[p]);
+				}
+#pragma unroll
+				for (int p = 0; p < UNR; p++) {
+					const int grp = base + p * (TMA_NW * 32) + tid;
+					if (grp < ngrp) xq_store_group8(xv, grp, xr[p]);
+				}
 			}
 		}
 		consumer_bar_sync();
 	}
+	if (tl >= 0) tl_begin(500 + a.epi); // timeline event: activations staged
 
 	const int kw = warp % KW, rw = warp / KW;
 	const int hA = (lane >> 2) & 1;
@@ -267,6 +296,7 @@ __global__ void __maxnreg__(96) matvec_idp_kernel(const IdpArgs ta) {
 			if (lane == 0) mbar_arrive(&empty[slot]);
 			if (++slot == NS) { slot = 0; phase ^= 1; }
 		}
+		if (tl >= 0 && tt < 4) tl_begin(510 + 10 * tt + a.epi); // timeline event: tile tt multiplied
 		// ---- lanes -> one sum per row (transposed butterfly: 6 shuffles for 4 rows), K-slices -> shared memory (fixed order) ----
 		{
 			const bool b4 = lane & 16, b3 = lane & 8;

@@ -75,6 +75,7 @@ static std::map<std::string, int>& tuning() {
 	    {"tma_short_rows", 1}, // rows of <= 64 pieces without a norm prologue: 16-row tiles with 1-2 K-slices (all lanes busy)
 	    {"tma_grid_even", 0}, // percent: shrink the persistent grid down to this fraction of the full one if that makes tiles % grid == 0
 	    {"tp_fused", 1},     // tensor parallel: fuse the two per-layer exchanges into the matvec kernels (push over NVLink + receive in the next prologue)
+	    {"idp_per_sm", 2},
 	    {"tail_prefetch_mb", 8}, // each decode kernel pulls this many MB of the NEXT kernel's first weights into L2 once its own loads are issued
 	    {"prefill_split", 3}, // batched prefill operand precision: 1 = fp16 x fp16 (fastest; logits drift ~4e-2 over 32 layers), 2 = hi+lo fp16
 	                          // activations, 3 = hi+lo on activations, weights and attention operands (default: logits within ~1e-3 of the decode path)
@@ -356,7 +357,7 @@ static int launch_matvec_idp(const MatvecArgs& a, cudaStream_t s, bool pdl) {
 	if (norm && a.n > 8192) return -1; // the norm-fused staging keeps one 32-element block per thread in registers
 	// two CTAs per SM when the staged activations leave room for >= 2 ring stages each (kernels overlap under PDL), else one deep ring
 	const size_t budget2 = (size_t) tune("tma_smem_kb") * 1024;
-	int NS = 0, per_sm = 2;
+	int NS = 0, per_sm = tune("idp_per_sm"); // 1: half the SM is left to the NEXT kernel, whose producer fills its ring while this one computes
 	for (int ns = tune("tma_ns_max"); ns >= 2; ns--)
 		if (idp_smem_bytes(t, a.n, ns) <= budget2) { NS = ns; break; }
 	if (!NS) {
