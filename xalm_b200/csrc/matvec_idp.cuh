@@ -18,17 +18,17 @@
 namespace xalm {
 
 constexpr int IDP_KW = 4, IDP_RW = 2, IDP_R = 4, IDP_RC = IDP_RW * IDP_R, IDP_U = 16;
-// Partial sums of the K-slice warps are handed to the tile's reducer warp through IDP_PB buffers, each with an mbarrier the 8 consumer
+// Partial sums of the K-slice warps are handed to the tile's reducer warp through PB buffers, each with an mbarrier the 8 consumer
 // warps arrive on: nobody but the reducer ever waits (a CTA-wide bar.sync per tile was 26 % of all stall cycles, profiles/r2_idp_ncu.md).
-// A buffer is reused IDP_PB tiles later; a warp cannot be more than NS (<= 5) tiles ahead of the reducer's own compute (ring), so 8 is safe.
-constexpr int IDP_PB = 8;
+// A buffer is reused PB tiles later; a warp cannot run more than NS stages (<= NS tiles) ahead of the slowest warp of its group (ring).
+__host__ __device__ inline int idp_pb(int NS) { return NS + 2 < 8 ? 8 : NS + 2; }
 constexpr int IDP_MP = 4; // staging passes of a norm-fused kernel: 8 elements x 256 lanes x 4 = n <= 8192
 
-__host__ __device__ inline size_t idp_smem_bytes(int type, int n, int NS) {
+__host__ __device__ inline size_t idp_smem_bytes(int type, int n, int NS, int NG = 1) {
 	size_t s = (xq_bytes(n) + 127) / 128 * 128;
 	s += (size_t) NS * IDP_RC * IDP_U * unit_bytes(type);
-	s += IDP_PB * IDP_KW * IDP_RC * sizeof(float); // partials, IDP_PB tiles deep
-	s += (2 * (size_t) NS + IDP_PB) * sizeof(uint64_t); // full / empty / partial barriers
+	s += (size_t) idp_pb(NS) * NG * IDP_KW * IDP_RC * sizeof(float); // partials, idp_pb(NS) tiles deep
+	s += (2 * (size_t) NS + idp_pb(NS)) * sizeof(uint64_t); // full / empty / partial barriers
 	s += 16 * sizeof(float);                    // reduction scratch
 	return s + 128;
 }
@@ -39,15 +39,21 @@ struct IdpArgs {
 	int n_tiles;    // virtual rows / 8
 };
 
-template <int TYPE, bool NORM>
-// <= 96 registers: the register file is per scheduler (16 K each), two CTAs of 9 warps need 5 warps on one of them: 16384 / 5 / 32 = 102
+// NG = consumer groups of 8 warps.  NG = 1: two CTAs per SM, each with its own staged activations and a 2-stage ring.  NG = 2: ONE CTA
+// per SM — the activations are fetched and quantised once per SM instead of twice (the broadcast read of x by every CTA is an L2
+// hot spot: 1-1.6 us) and the shared memory that bought goes to the ring (6 stages instead of 2 x 2), so the producer keeps HBM busy
+// through the dependency wait + staging of the consumers.  The two groups take alternate ring stages.
+template <int TYPE, bool NORM, int NG>
+// <= 96 registers: the register file is per scheduler (16 K each); 17 warps (or two CTAs of 9) put 5 warps on one of them: 16384 / 5 / 32 = 102
 __global__ void __maxnreg__(96) matvec_idp_kernel(const IdpArgs ta) {
 	using F = IdpFmt<TYPE>;
 	constexpr int KW = IDP_KW, R = IDP_R, RC = IDP_RC, U = IDP_U, UB = F::UB;
+	constexpr int NCW = NG * TMA_NW, NT = NCW * 32; // consumer warps / threads
+	auto cbar = [] { if (NG == 1) asm volatile("bar.sync 1, 256;" ::: "memory"); else asm volatile("bar.sync 1, 512;" ::: "memory"); };
 	constexpr int ROW_STAGE = U * UB;
 	constexpr int SLOT = RC * ROW_STAGE;
 	const MatvecArgs& a = ta.a;
-	const int NS = ta.NS;
+	const int NS = ta.NS, PB = idp_pb(ta.NS);
 	const int n = a.n, nu = n / 256, nb_row = n / 32;
 	const int kranges = (nu + U - 1) / U;
 
@@ -55,7 +61,7 @@ __global__ void __maxnreg__(96) matvec_idp_kernel(const IdpArgs ta) {
 	uint8_t* xq_base = smem;
 	uint8_t* ring = smem + (xq_bytes(n) + 127) / 128 * 128;
 	float* part = reinterpret_cast<float*>(ring + (size_t) NS * SLOT);
-	float* s_red = part + IDP_PB * KW * RC;
+	float* s_red = part + PB * NG * KW * RC;
 	uint64_t* full = reinterpret_cast<uint64_t*>(s_red + 16);
 	uint64_t* empty = full + NS;
 	uint64_t* pbar = empty + NS;
@@ -66,7 +72,7 @@ __global__ void __maxnreg__(96) matvec_idp_kernel(const IdpArgs ta) {
 			mbar_init(&full[s], 1);
 			mbar_init(&empty[s], TMA_NW);
 		}
-		for (int s = 0; s < IDP_PB; s++) mbar_init(&pbar[s], TMA_NW);
+		for (int s = 0; s < PB; s++) mbar_init(&pbar[s], (kranges >= NG ? NG : 1) * TMA_NW); // the warps that hold a piece of a tile
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
@@ -76,7 +82,7 @@ __global__ void __maxnreg__(96) matvec_idp_kernel(const IdpArgs ta) {
 
 	const int my_tiles = ((int) blockIdx.x < ta.n_tiles) ? (ta.n_tiles - 1 - (int) blockIdx.x) / (int) gridDim.x + 1 : 0;
 
-	if (warp == TMA_NW) {
+	if (warp == NCW) {
 		// ===================== producer: weights only — runs ahead of griddepcontrol.wait =====================
 		if (lane == 0) {
 			int slot = 0, phase = 0;
@@ -125,11 +131,12 @@ __global__ void __maxnreg__(96) matvec_idp_kernel(const IdpArgs ta) {
 	// not depend on the previous kernel: request them before the dependency wait (host: NORM only with n <= 8192 = IDP_MP passes).
 	const int tid = threadIdx.x;
 	const int ngrp = n / 8;
-	uint4 gw[NORM ? IDP_MP : 1][2];
+	constexpr int MP = IDP_MP / NG; // staging passes of a norm-fused kernel (n <= 8192)
+	uint4 gw[NORM ? MP : 1][2];
 	if (NORM) {
 #pragma unroll
-		for (int p = 0; p < IDP_MP; p++) {
-			const int grp = p * (TMA_NW * 32) + tid;
+		for (int p = 0; p < MP; p++) {
+			const int grp = p * NT + tid;
 			if (grp < ngrp) {
 				if (a.norm_type == XALM_F32) {
 					gw[p][0] = *reinterpret_cast<const uint4*>(reinterpret_cast<const float*>(a.norm_w) + grp * 8);
@@ -144,7 +151,7 @@ __global__ void __maxnreg__(96) matvec_idp_kernel(const IdpArgs ta) {
 	tl_mark(tl, 2);
 	if (a.epi == EPI_QKV && blockIdx.x == 0 && a.step->kv_sink > 0) {
 		const int pairs = a.kv_dim / 2;
-		for (int i = threadIdx.x; i < a.step->kv_sink * pairs; i += TMA_NW * 32) {
+		for (int i = threadIdx.x; i < a.step->kv_sink * pairs; i += NT) {
 			const int r = i / pairs, p = i % pairs;
 			__half2* kp = reinterpret_cast<__half2*>(a.k_cache + (size_t) r * a.kv_dim) + p;
 			float2 v = __half22float2(*kp);
@@ -160,7 +167,7 @@ __global__ void __maxnreg__(96) matvec_idp_kernel(const IdpArgs ta) {
 			const unsigned int seq = a.step->ar_base + (unsigned int) a.recv_idx + 1u;
 			const int chunk = ((n / 4 + n_red - 1) / n_red) * 4;
 			const int i0 = (int) blockIdx.x * chunk, i1 = min(n, i0 + chunk);
-			for (int i = i0 + (int) threadIdx.x * 4; i < i1; i += TMA_NW * 32 * 4) {
+			for (int i = i0 + (int) threadIdx.x * 4; i < i1; i += NT * 4) {
 				float4 v = ld_act4(a.x + i);
 				float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
 				for (int p = 0; p < a.n_recv; p++) {
@@ -206,31 +213,33 @@ __global__ void __maxnreg__(96) matvec_idp_kernel(const IdpArgs ta) {
 			}
 		};
 		if (NORM) {
-			float xr[IDP_MP][8];
+			float xr[MP][8];
 			float ss = 0.f;
 #pragma unroll
-			for (int p = 0; p < IDP_MP; p++) {
-				const int grp = p * (TMA_NW * 32) + tid;
+			for (int p = 0; p < MP; p++) {
+				const int grp = p * NT + tid;
 				if (grp < ngrp) load_group(grp, xr[p]);
 			}
 #pragma unroll
-			for (int p = 0; p < IDP_MP; p++) {
-				const int grp = p * (TMA_NW * 32) + tid;
+			for (int p = 0; p < MP; p++) {
+				const int grp = p * NT + tid;
 				if (grp < ngrp) {
 #pragma unroll
 					for (int e = 0; e < 8; e++) ss += xr[p][e] * xr[p][e];
 				}
 			}
 			ss = warp_sum(ss);
+			if (tl >= 0) tl_begin(600 + a.epi); // event: x arrived
 			if (lane == 0) s_red[warp] = ss;
-			consumer_bar_sync();
+			cbar();
+			if (tl >= 0) tl_begin(610 + a.epi); // event: sum of squares known
 			float tot = 0.f;
 #pragma unroll
-			for (int i = 0; i < TMA_NW; i++) tot += s_red[i];
+			for (int i = 0; i < NCW; i++) tot += s_red[i];
 			const float scale = 1.0f / sqrtf(tot / (float) n + a.norm_eps);
 #pragma unroll
-			for (int p = 0; p < IDP_MP; p++) {
-				const int grp = p * (TMA_NW * 32) + tid;
+			for (int p = 0; p < MP; p++) {
+				const int grp = p * NT + tid;
 				if (grp < ngrp) { // (warp-uniform: n % 256 == 0)
 #pragma unroll
 					for (int e = 0; e < 8; e++) {
@@ -250,52 +259,62 @@ __global__ void __maxnreg__(96) matvec_idp_kernel(const IdpArgs ta) {
 				}
 			}
 		} else {
-			constexpr int UNR = 4; // groups in flight per lane
-			for (int base = 0; base < ngrp; base += UNR * TMA_NW * 32) {
+			constexpr int UNR = 4 / NG; // groups in flight per lane
+			for (int base = 0; base < ngrp; base += UNR * NT) {
 				float xr[UNR][8];
 #pragma unroll
 				for (int p = 0; p < UNR; p++) {
-					const int grp = base + p * (TMA_NW * 32) + tid;
+					const int grp = base + p * NT + tid;
 					if (grp < ngrp) load_group(grp, xr[p]);
 				}
 #pragma unroll
 				for (int p = 0; p < UNR; p++) {
-					const int grp = base + p * (TMA_NW * 32) + tid;
+					const int grp = base + p * NT + tid;
 					if (grp < ngrp) xq_store_group8(xv, grp, xr[p]);
 				}
 			}
 		}
-		consumer_bar_sync();
+		cbar();
 	}
 	if (tl >= 0) tl_begin(500 + a.epi); // timeline event: activations staged
 
-	const int kw = warp % KW, rw = warp / KW;
+	const int cg = warp / TMA_NW, wl = warp % TMA_NW; // consumer group, warp within it
+	const int kw = wl % KW, rw = wl / KW;
 	const int hA = (lane >> 2) & 1;
-	int slot = 0, phase = 0;
+	const bool both = kranges >= NG; // every group holds a piece of every tile (else tiles alternate between the groups)
+	int slot = 0, phase = 0, gi = 0; // gi: stage counter of the CTA; group gi % NG takes it
+	int pb_next = 0, pph_next = 0;   // partial buffer of the tile and the phase of its barrier (tt % PB, (tt / PB) & 1 without the divisions)
 	for (int tt = 0; tt < my_tiles; tt++) {
+		const int pb = pb_next, pph = pph_next;
+		if (++pb_next == PB) { pb_next = 0; pph_next ^= 1; }
 		const int row0 = ((int) blockIdx.x + tt * (int) gridDim.x) * RC;
-		const bool reducer = warp == (tt % TMA_NW);
+		const int g_last = (gi + kranges - 1) % NG; // the group that takes the tile's last stage supplies the reducer
+		const bool mine = both || (gi % NG) == cg;
+		const bool reducer = cg == g_last && wl == ((tt / (both ? 1 : NG)) % TMA_NW);
 		float xold = 0.f; // residual: the reducer warp fetches the old activation now, so its epilogue does not sit on an L2 round trip
 		if (a.epi == EPI_RESIDUAL && reducer && lane < RC && row0 + lane < a.d) xold = a.out[row0 + lane];
 		float y[R];
 #pragma unroll
 		for (int r = 0; r < R; r++) y[r] = 0.f;
-		for (int kr = 0; kr < kranges; kr++) {
-			const int u0 = kr * U;
-			const int nb = 8 * min(U, nu - u0); // blocks per row in this stage
-			const int b = kw * 32 + lane;
-			mbar_wait(&full[slot], phase);
-			if (b < nb) {
-				XqBlock xb;
-				xq_load(xv, u0 * 8 + b, hA, xb);
-				const uint8_t* unit = ring + (size_t) slot * SLOT + (size_t) (rw * R) * ROW_STAGE + (size_t) (b >> 3) * UB;
+		for (int kr = 0; kr < kranges; kr++, gi++) {
+			if (NG == 1 || (gi % NG) == cg) {
+				const int u0 = kr * U;
+				const int nb = 8 * min(U, nu - u0); // blocks per row in this stage
+				const int b = kw * 32 + lane;
+				mbar_wait(&full[slot], phase);
+				if (b < nb) {
+					XqBlock xb;
+					xq_load(xv, u0 * 8 + b, hA, xb);
+					const uint8_t* unit = ring + (size_t) slot * SLOT + (size_t) (rw * R) * ROW_STAGE + (size_t) (b >> 3) * UB;
 #pragma unroll
-				for (int r = 0; r < R; r++) F::block(unit + (size_t) r * ROW_STAGE, b & 7, hA, xb, y[r]);
+					for (int r = 0; r < R; r++) F::block(unit + (size_t) r * ROW_STAGE, b & 7, hA, xb, y[r]);
+				}
+				__syncwarp();
+				if (lane == 0) mbar_arrive(&empty[slot]);
 			}
-			__syncwarp();
-			if (lane == 0) mbar_arrive(&empty[slot]);
 			if (++slot == NS) { slot = 0; phase ^= 1; }
 		}
+		if (!mine) continue;
 		if (tl >= 0 && tt < 4) tl_begin(510 + 10 * tt + a.epi); // timeline event: tile tt multiplied
 		// ---- lanes -> one sum per row (transposed butterfly: 6 shuffles for 4 rows), K-slices -> shared memory (fixed order) ----
 		{
@@ -310,17 +329,21 @@ __global__ void __maxnreg__(96) matvec_idp_kernel(const IdpArgs ta) {
 			k += __shfl_xor_sync(0xffffffffu, k, 4);
 			k += __shfl_xor_sync(0xffffffffu, k, 2);
 			k += __shfl_xor_sync(0xffffffffu, k, 1);
-			if ((lane & 7) == 0) part[(tt % IDP_PB) * (KW * RC) + kw * RC + rw * R + (b4 ? 2 : 0) + (b3 ? 1 : 0)] = k;
+			if ((lane & 7) == 0) part[(pb * NG + cg) * (KW * RC) + kw * RC + rw * R + (b4 ? 2 : 0) + (b3 ? 1 : 0)] = k;
 		}
 		__syncwarp();
-		if (lane == 0) mbar_arrive(&pbar[tt % IDP_PB]); // (release: this warp's partial sums are visible to whoever completes the wait)
+		if (lane == 0) mbar_arrive(&pbar[pb]); // (release: this warp's partial sums are visible to whoever completes the wait)
 		if (reducer) { // rotating reducer: lane i owns row i of the tile
-			mbar_wait(&pbar[tt % IDP_PB], (tt / IDP_PB) & 1);
-			const float* pt = part + (tt % IDP_PB) * (KW * RC);
+			mbar_wait(&pbar[pb], pph);
 			float yv = 0.f;
 			if (lane < RC) {
 #pragma unroll
-				for (int k = 0; k < KW; k++) yv += pt[k * RC + lane];
+				for (int g = 0; g < NG; g++) {
+					if (!both && g != cg) continue;
+					const float* pt = part + (pb * NG + g) * (KW * RC);
+#pragma unroll
+					for (int k = 0; k < KW; k++) yv += pt[k * RC + lane];
+				}
 			}
 			const float ynext = __shfl_down_sync(0xffffffffu, yv, 1);
 			if (a.epi == EPI_RESIDUAL) {

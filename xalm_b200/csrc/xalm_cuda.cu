@@ -76,6 +76,7 @@ static std::map<std::string, int>& tuning() {
 	    {"tma_grid_even", 0}, // percent: shrink the persistent grid down to this fraction of the full one if that makes tiles % grid == 0
 	    {"tp_fused", 1},     // tensor parallel: fuse the two per-layer exchanges into the matvec kernels (push over NVLink + receive in the next prologue)
 	    {"idp_per_sm", 2},
+	    {"idp_ng", 0},      // consumer groups per CTA of the integer-dot matvec: 0 = by format, 2 = one 17-warp CTA per SM, 1 = two 9-warp CTAs
 	    {"tail_prefetch_mb", 8}, // each decode kernel pulls this many MB of the NEXT kernel's first weights into L2 once its own loads are issued
 	    {"prefill_split", 3}, // batched prefill operand precision: 1 = fp16 x fp16 (fastest; logits drift ~4e-2 over 32 layers), 2 = hi+lo fp16
 	                          // activations, 3 = hi+lo on activations, weights and attention operands (default: logits within ~1e-3 of the decode path)
@@ -321,28 +322,30 @@ static int launch_matvec_tma(const MatvecArgs& a, cudaStream_t s, bool pdl) {
 // ---------------------------------------------------------------------------------------------------------
 // integer-dot matvec dispatch (matvec_idp.cuh): the integer weight formats in unit layout
 // ---------------------------------------------------------------------------------------------------------
-template <int TYPE, bool NORM>
+template <int TYPE, bool NORM, int NG>
 static cudaError_t launch_idp_inst(const IdpArgs& ta, size_t smem, int max_ctas_per_sm, cudaStream_t s, bool pdl) {
 	static std::map<std::pair<int, size_t>, int> occ_cache;
-	auto kern = matvec_idp_kernel<TYPE, NORM>;
-	cudaError_t e = ensure_smem_attr(kern, 220 * 1024);
+	auto kern = matvec_idp_kernel<TYPE, NORM, NG>;
+	constexpr int threads = (NG * TMA_NW + 1) * 32;
+	cudaError_t e = ensure_smem_attr(kern, 227 * 1024);
 	if (e != cudaSuccess) return e;
 	const std::pair<int, size_t> key(current_device(), smem);
 	auto it = occ_cache.find(key);
 	if (it == occ_cache.end()) {
 		int occ = 1;
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, (TMA_NW + 1) * 32, smem);
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem);
 		if (e != cudaSuccess) return e;
 		it = occ_cache.emplace(key, occ < 1 ? 1 : occ).first;
 	}
 	const int per_sm = it->second < max_ctas_per_sm ? it->second : max_ctas_per_sm;
 	int grid = num_sms() * per_sm; // persistent: exactly the CTAs that can be resident at once
 	if (grid > ta.n_tiles) grid = ta.n_tiles;
-	return launch_smem(kern, dim3(grid), dim3((TMA_NW + 1) * 32), smem, s, pdl, ta);
+	return launch_smem(kern, dim3(grid), dim3(threads), smem, s, pdl, ta);
 }
 template <int TYPE>
-static cudaError_t launch_idp_typed(const IdpArgs& ta, bool norm, size_t smem, int per_sm, cudaStream_t s, bool pdl) {
-	return norm ? launch_idp_inst<TYPE, true>(ta, smem, per_sm, s, pdl) : launch_idp_inst<TYPE, false>(ta, smem, per_sm, s, pdl);
+static cudaError_t launch_idp_typed(const IdpArgs& ta, bool norm, int ng, size_t smem, int per_sm, cudaStream_t s, bool pdl) {
+	if (ng == 2) return norm ? launch_idp_inst<TYPE, true, 2>(ta, smem, 1, s, pdl) : launch_idp_inst<TYPE, false, 2>(ta, smem, 1, s, pdl);
+	return norm ? launch_idp_inst<TYPE, true, 1>(ta, smem, per_sm, s, pdl) : launch_idp_inst<TYPE, false, 1>(ta, smem, per_sm, s, pdl);
 }
 // returns -1 when the matrix cannot go down this path (the caller falls back to the float kernels)
 static int launch_matvec_idp(const MatvecArgs& a, cudaStream_t s, bool pdl) {
@@ -354,31 +357,43 @@ static int launch_matvec_idp(const MatvecArgs& a, cudaStream_t s, bool pdl) {
 	const int vrows = a.epi == EPI_GLU ? 2 * a.d : a.d;
 	if (a.n % 256 || vrows % IDP_RC) return -1;
 	const bool norm = a.norm_w != nullptr;
-	if (norm && a.n > 8192) return -1; // the norm-fused staging keeps one 32-element block per thread in registers
-	// two CTAs per SM when the staged activations leave room for >= 2 ring stages each (kernels overlap under PDL), else one deep ring
-	const size_t budget2 = (size_t) tune("tma_smem_kb") * 1024;
-	int NS = 0, per_sm = tune("idp_per_sm"); // 1: half the SM is left to the NEXT kernel, whose producer fills its ring while this one computes
-	for (int ns = tune("tma_ns_max"); ns >= 2; ns--)
-		if (idp_smem_bytes(t, a.n, ns) <= budget2) { NS = ns; break; }
-	if (!NS) {
-		per_sm = 1;
-		for (int ns = 5; ns >= 2; ns--)
-			if (idp_smem_bytes(t, a.n, ns) <= 216 * 1024) { NS = ns; break; }
+	if (norm && a.n > 8192) return -1; // the norm-fused staging keeps its 8-element groups in registers (IDP_MP passes)
+	int NS = 0, per_sm = 1, ng = tune("idp_ng");
+	if (ng == 0) ng = unit_bytes(t) >= 256 ? 2 : 1; // the 4/5-bit formats are bound by the consumers, not by the ring depth: measured faster as two CTAs
+	if (ng == 2) { // one CTA per SM, two consumer groups, the whole shared memory behind one copy of the activations
+		// NS even: a slot then always serves the same group (a group that skipped a completion of a slot's barrier could not tell
+		// the phase it waits for from the one before it: mbarrier waits carry one parity bit)
+		for (int ns = 12; ns >= 4; ns -= 2)
+			if (idp_smem_bytes(t, a.n, ns, 2) <= 226 * 1024) { NS = ns; break; }
+		if (!NS) ng = 1;
+	}
+	if (ng != 2) {
+		ng = 1;
+		// two CTAs per SM when the staged activations leave room for >= 2 ring stages each (kernels overlap under PDL), else one deep ring
+		const size_t budget2 = (size_t) tune("tma_smem_kb") * 1024;
+		per_sm = tune("idp_per_sm");
+		for (int ns = tune("tma_ns_max"); ns >= 2; ns--)
+			if (idp_smem_bytes(t, a.n, ns) <= budget2) { NS = ns; break; }
+		if (!NS) {
+			per_sm = 1;
+			for (int ns = 5; ns >= 2; ns--)
+				if (idp_smem_bytes(t, a.n, ns) <= 216 * 1024) { NS = ns; break; }
+		}
 	}
 	if (!NS) return -1;
 	IdpArgs ta;
 	ta.a = a;
 	ta.NS = NS;
 	ta.n_tiles = vrows / IDP_RC;
-	const size_t smem = idp_smem_bytes(t, a.n, NS);
+	const size_t smem = idp_smem_bytes(t, a.n, NS, ng);
 	cudaError_t e;
 	switch (t) {
-		case XALM_Q8_0: e = launch_idp_typed<XALM_Q8_0>(ta, norm, smem, per_sm, s, pdl); break;
-		case XALM_Q8: e = launch_idp_typed<XALM_Q8>(ta, norm, smem, per_sm, s, pdl); break;
-		case XALM_Q4_0: e = launch_idp_typed<XALM_Q4_0>(ta, norm, smem, per_sm, s, pdl); break;
-		case XALM_Q4_1: e = launch_idp_typed<XALM_Q4_1>(ta, norm, smem, per_sm, s, pdl); break;
-		case XALM_Q5_0: e = launch_idp_typed<XALM_Q5_0>(ta, norm, smem, per_sm, s, pdl); break;
-		case XALM_Q5_1: e = launch_idp_typed<XALM_Q5_1>(ta, norm, smem, per_sm, s, pdl); break;
+		case XALM_Q8_0: e = launch_idp_typed<XALM_Q8_0>(ta, norm, ng, smem, per_sm, s, pdl); break;
+		case XALM_Q8: e = launch_idp_typed<XALM_Q8>(ta, norm, ng, smem, per_sm, s, pdl); break;
+		case XALM_Q4_0: e = launch_idp_typed<XALM_Q4_0>(ta, norm, ng, smem, per_sm, s, pdl); break;
+		case XALM_Q4_1: e = launch_idp_typed<XALM_Q4_1>(ta, norm, ng, smem, per_sm, s, pdl); break;
+		case XALM_Q5_0: e = launch_idp_typed<XALM_Q5_0>(ta, norm, ng, smem, per_sm, s, pdl); break;
+		case XALM_Q5_1: e = launch_idp_typed<XALM_Q5_1>(ta, norm, ng, smem, per_sm, s, pdl); break;
 		default: return -1;
 	}
 	if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "matvec (idp) launch failed: %s", cudaGetErrorString(e));
