@@ -154,6 +154,8 @@ struct WMat {
 	int n = 0;
 	int flags = 0; // bit0: fp8 tensor contains codes an IEEE decoder maps to NaN/Inf -> take the exact LUT path
 	int layout_units = 0; // block format stored unit-interleaved for the TMA kernel (matvec_tma.cuh) instead of planar
+	int layout_frag = 0;  // integer format stored as fragment tiles (frag_layout.cuh): p0 = records, s0 = bytes of one 16-row tile
+	int glu_half = 0;     // fragment tiles of a gate|up matrix: rows [0, glu_half) are W1, the rest W3, interleaved 8 + 8 per tile
 	const uint8_t* p0 = nullptr;
 	const uint8_t* p1 = nullptr;
 	const uint8_t* p2 = nullptr;

@@ -55,6 +55,11 @@ struct MatvecArgs {
 	const uint8_t* pf_ptr;       // next kernel's weights (or nullptr)
 	unsigned long long pf_bytes;
 	int pf_kv;                   // 1: also prefetch rows [0, kv_len) of k_cache / v_cache (the attention kernel that follows QKV)
+	// rmsnorm weights of the NEXT norm-fused kernel (read once per token, i.e. from DRAM): CTA 0 pulls them into L2 at entry.  That
+	// kernel requests them before its dependency wait; coming from DRAM behind its own weight stream they took ~2.5 us, and the
+	// activation loads issued after them return in order behind them (profiles/r2_decode_timeline.md)
+	const uint8_t* pf_norm_ptr;
+	unsigned int pf_norm_bytes;
 	// tensor-parallel exchange fused into the matvec kernels (matvec_tma.cuh), LL style: the row-split matvecs (Wo, W2) PUSH every
 	// partial row as an 8-byte {value, sequence tag} word straight into every rank's receive slot over NVLink (posted stores, no
 	// fence, no flag, no extra kernel); the next kernel's rmsnorm prologue polls the tags of the words it needs and adds the

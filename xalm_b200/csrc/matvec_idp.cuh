@@ -85,6 +85,8 @@ __global__ void __maxnreg__(96) matvec_idp_kernel(const IdpArgs ta) {
 	if (warp == NCW) {
 		// ===================== producer: weights only — runs ahead of griddepcontrol.wait =====================
 		if (lane == 0) {
+			if (blockIdx.x == 0 && a.pf_norm_ptr && a.pf_norm_bytes >= 16)
+				asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.pf_norm_ptr), "r"(a.pf_norm_bytes & ~15u) : "memory");
 			int slot = 0, phase = 0;
 			for (int tt = 0; tt < my_tiles; tt++) {
 				const int row0 = ((int) blockIdx.x + tt * (int) gridDim.x) * RC;
@@ -231,12 +233,8 @@ __global__ void __maxnreg__(96) matvec_idp_kernel(const IdpArgs ta) {
 			ss = warp_sum(ss);
 			if (tl >= 0) tl_begin(600 + a.epi); // event: x arrived
 			if (lane == 0) s_red[warp] = ss;
-			cbar();
-			if (tl >= 0) tl_begin(610 + a.epi); // event: sum of squares known
-			float tot = 0.f;
-#pragma unroll
-			for (int i = 0; i < NCW; i++) tot += s_red[i];
-			const float scale = 1.0f / sqrtf(tot / (float) n + a.norm_eps);
+			// The staged vector is x * g; the scalar 1/rms is applied to the row sums in the epilogue (y = scale * sum w * (x * g)), so
+			// the staging does not wait for the CTA-wide sum of squares: one barrier instead of two between x arriving and the first tile
 #pragma unroll
 			for (int p = 0; p < MP; p++) {
 				const int grp = p * NT + tid;
@@ -253,13 +251,13 @@ __global__ void __maxnreg__(96) matvec_idp_kernel(const IdpArgs ta) {
 							const uint32_t u = h == 0 ? q.x : h == 1 ? q.y : h == 2 ? q.z : q.w;
 							g = __uint_as_float((e & 1) ? (u & 0xFFFF0000u) : (u << 16));
 						}
-						xr[p][e] = xr[p][e] * scale * g; // infer.cpp:233-235
+						xr[p][e] = xr[p][e] * g; // infer.cpp:233-235 without the scalar
 					}
 					xq_store_group8(xv, grp, xr[p]);
 				}
 			}
 		} else {
-			constexpr int UNR = 4 / NG; // groups in flight per lane
+			constexpr int UNR = 4; // groups in flight per lane (n = 14336 on 512 threads: one round of loads)
 			for (int base = 0; base < ngrp; base += UNR * NT) {
 				float xr[UNR][8];
 #pragma unroll
@@ -275,6 +273,13 @@ __global__ void __maxnreg__(96) matvec_idp_kernel(const IdpArgs ta) {
 			}
 		}
 		cbar();
+	}
+	float nscale = 1.f; // 1/rms of the input (infer.cpp:229-232), applied to the row sums
+	if (NORM) {
+		float tot = 0.f;
+#pragma unroll
+		for (int i = 0; i < NCW; i++) tot += s_red[i];
+		nscale = 1.0f / sqrtf(tot / (float) n + a.norm_eps);
 	}
 	if (tl >= 0) tl_begin(500 + a.epi); // timeline event: activations staged
 
@@ -345,6 +350,7 @@ __global__ void __maxnreg__(96) matvec_idp_kernel(const IdpArgs ta) {
 					for (int k = 0; k < KW; k++) yv += pt[k * RC + lane];
 				}
 			}
+			if (NORM) yv *= nscale;
 			const float ynext = __shfl_down_sync(0xffffffffu, yv, 1);
 			if (a.epi == EPI_RESIDUAL) {
 				if (lane < RC && row0 + lane < a.d) a.out[row0 + lane] = xold + yv;

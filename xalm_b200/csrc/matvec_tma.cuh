@@ -199,6 +199,8 @@ __global__ void __launch_bounds__((TMA_NW + 1) * 32, 1) matvec_tma_kernel(const 
 	if (warp == TMA_NW) {
 		// ===================== producer: weights only — runs ahead of griddepcontrol.wait =====================
 		if (lane == 0) {
+			if (blockIdx.x == 0 && a.pf_norm_ptr && a.pf_norm_bytes >= 16) // the next norm-fused kernel's rmsnorm weights -> L2 (matvec.cuh)
+				asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.pf_norm_ptr), "r"(a.pf_norm_bytes & ~15u) : "memory");
 			int slot = 0, phase = 0;
 			for (int tt = 0; tt < my_tiles; tt++) {
 				const int row0 = ((int) blockIdx.x + tt * (int) gridDim.x) * RC;

@@ -40,6 +40,7 @@
 #include <vector>
 
 #include "matvec.cuh"
+#include "frag_layout.cuh"
 #include "prefill.h"
 
 namespace xalm {
@@ -92,10 +93,14 @@ __device__ __forceinline__ void store_a8(const ATiles& a, int m, int k0, const f
 __device__ __forceinline__ float ld_h(const uint8_t* p) { return __half2float(*reinterpret_cast<const __half*>(p)); }
 
 // 8 consecutive elements k0..k0+7 (k0 % 8 == 0) of physical row `r`
-// TT: compile-time type (the switch folds away) or -1 for "whatever w.type says"; LU: 1 = unit-interleaved, 0 = planar, -1 = runtime
+// TT: compile-time type (the switch folds away) or -1 for "whatever w.type says"; LU: 2 = fragment tiles, 1 = unit-interleaved, 0 = planar, -1 = runtime
 template <int TT, int LU>
 __device__ __forceinline__ void wmat_decode8(const WMat& w, int r, int k0, float (&v)[8]) {
 	const int t = TT >= 0 ? TT : w.type;
+	if (LU == 2 || (LU < 0 && w.layout_frag)) { // fragment tiles of the tensor-core decode matvec (frag_layout.cuh)
+		frag_decode8(w, t, r, k0, v);
+		return;
+	}
 	const uint8_t* row = w.p0 + (size_t) r * w.s0;
 	switch (t) {
 		case XALM_F32: {
@@ -1402,7 +1407,9 @@ static int launch_dequant_tiles(const WMat& w, bool glu, int glu_off, int n_vali
 	const int grid = (int) std::min<size_t>((chunks + 255) / 256, (size_t) sm_count() * 16);
 	// the common formats get a kernel with the type and layout folded in at compile time (2x the generic one's throughput)
 #define XALM_DQ(TT, LU) dequant_tiles_kernel<TT, LU><<<grid, 256, 0, s>>>(w, glu ? 1 : 0, glu_off, n_valid, K, NT, KT, dst, dst_lo)
-	if (w.type == XALM_Q8_0 && w.layout_units) XALM_DQ(XALM_Q8_0, 1);
+	if (w.type == XALM_Q8_0 && w.layout_frag) XALM_DQ(XALM_Q8_0, 2);
+	else if (w.type == XALM_Q4_0 && w.layout_frag) XALM_DQ(XALM_Q4_0, 2);
+	else if (w.type == XALM_Q8_0 && w.layout_units) XALM_DQ(XALM_Q8_0, 1);
 	else if (w.type == XALM_Q4_0 && w.layout_units) XALM_DQ(XALM_Q4_0, 1);
 	else if (w.type == XALM_F16) XALM_DQ(XALM_F16, 0);
 	else if (w.type == XALM_BF16) XALM_DQ(XALM_BF16, 0);

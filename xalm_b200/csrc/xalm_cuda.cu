@@ -28,6 +28,7 @@
 #include "matvec.cuh"
 #include "matvec_tma.cuh"
 #include "matvec_idp.cuh"
+#include "matvec_mma.cuh"
 #include "decode_mega.h"
 #include "prefill.h"
 
@@ -76,7 +77,8 @@ static std::map<std::string, int>& tuning() {
 	    {"tma_grid_even", 0}, // percent: shrink the persistent grid down to this fraction of the full one if that makes tiles % grid == 0
 	    {"tp_fused", 1},     // tensor parallel: fuse the two per-layer exchanges into the matvec kernels (push over NVLink + receive in the next prologue)
 	    {"idp_per_sm", 2},
-	    {"idp_ng", 0},      // consumer groups per CTA of the integer-dot matvec: 0 = by format, 2 = one 17-warp CTA per SM, 1 = two 9-warp CTAs
+	    {"mma", 1},         // integer formats: fragment-tile layout + tensor-core (mma.sync int8) matvec (matvec_mma.cuh); 0 = unit layout + dp4a
+    {"idp_ng", 0},      // consumer groups per CTA of the integer-dot matvec: 0 = by format, 2 = one 17-warp CTA per SM, 1 = two 9-warp CTAs
 	    {"tail_prefetch_mb", 8}, // each decode kernel pulls this many MB of the NEXT kernel's first weights into L2 once its own loads are issued
 	    {"prefill_split", 3}, // batched prefill operand precision: 1 = fp16 x fp16 (fastest; logits drift ~4e-2 over 32 layers), 2 = hi+lo fp16
 	                          // activations, 3 = hi+lo on activations, weights and attention operands (default: logits within ~1e-3 of the decode path)
@@ -400,6 +402,51 @@ static int launch_matvec_idp(const MatvecArgs& a, cudaStream_t s, bool pdl) {
 	return XALM_OK;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// tensor-core matvec dispatch (matvec_mma.cuh): the integer weight formats in fragment tiles
+// ---------------------------------------------------------------------------------------------------------
+template <int TYPE, bool NORM>
+static cudaError_t launch_mma_inst(const MmaArgs& ta, size_t smem, cudaStream_t s, bool pdl) {
+	auto kern = matvec_mma_kernel<TYPE, NORM>;
+	cudaError_t e = ensure_smem_attr(kern, 227 * 1024);
+	if (e != cudaSuccess) return e;
+	int grid = num_sms(); // persistent: one CTA per SM
+	if (grid > ta.n_tiles) grid = ta.n_tiles;
+	return launch_smem(kern, dim3(grid), dim3((MMA_NCW + 1) * 32), smem, s, pdl, ta);
+}
+static int launch_matvec_mma(const MatvecArgs& a, cudaStream_t s, bool pdl) {
+	const int t = a.w.type;
+	const int vrows = a.epi == EPI_GLU ? 2 * a.d : a.d;
+	if (!mma_supported(t) || a.n % 32 || vrows % MMA_RC || vrows != a.w.rows)
+		return set_error(XALM_ERR_STATE, "matrix is in fragment layout but the tensor-core matvec cannot take it (type=%d n=%d rows=%d)", t, a.n, vrows);
+	if ((a.epi == EPI_GLU) != (a.w.glu_half != 0))
+		return set_error(XALM_ERR_STATE, "fragment layout: gate|up interleave (%d) does not match the epilogue (%d)", a.w.glu_half, a.epi);
+	const bool norm = a.norm_w != nullptr;
+	int NS = 0;
+	for (int ns = 8; ns >= 2; ns--)
+		if (mma_smem_bytes(t, a.n, ns) <= 226 * 1024) { NS = ns; break; }
+	if (!NS) return set_error(XALM_ERR_UNSUPPORTED, "matmul: rows of %d elements do not fit the tensor-core matvec's shared memory", a.n);
+	MmaArgs ta;
+	ta.a = a;
+	ta.NS = NS;
+	ta.n_tiles = vrows / MMA_RC;
+	const size_t smem = mma_smem_bytes(t, a.n, NS);
+	cudaError_t e;
+#define XALM_MMA_CASE(T) case T: e = norm ? launch_mma_inst<T, true>(ta, smem, s, pdl) : launch_mma_inst<T, false>(ta, smem, s, pdl); break;
+	switch (t) {
+		XALM_MMA_CASE(XALM_Q8_0)
+		XALM_MMA_CASE(XALM_Q8)
+		XALM_MMA_CASE(XALM_Q4_0)
+		XALM_MMA_CASE(XALM_Q4_1)
+		XALM_MMA_CASE(XALM_Q5_0)
+		XALM_MMA_CASE(XALM_Q5_1)
+		default: return set_error(XALM_ERR_STATE, "fragment layout with type %d", t);
+	}
+#undef XALM_MMA_CASE
+	if (e != cudaSuccess) return set_error(XALM_ERR_CUDA, "matvec (mma) launch failed: %s", cudaGetErrorString(e));
+	return XALM_OK;
+}
+
 static int launch_matvec(MatvecArgs a, cudaStream_t s, bool pdl) {
 	const bool norm = a.norm_w != nullptr;
 	if (norm && a.norm_type != XALM_F32 && a.norm_type != XALM_BF16)
@@ -409,6 +456,7 @@ static int launch_matvec(MatvecArgs a, cudaStream_t s, bool pdl) {
 	const int vrows = a.epi == EPI_GLU ? 2 * a.d : a.d;
 	int t = a.w.type;
 	cudaError_t e;
+	if (a.w.layout_frag) return launch_matvec_mma(a, s, pdl);
 	{
 		const int rc = launch_matvec_idp(a, s, pdl);
 		if (rc >= 0) return rc;
@@ -682,10 +730,21 @@ struct WSlot {
 	bool allocated = false;
 };
 
-static int alloc_wmat(DevAlloc& da, WMat& m, int type, int rows, int n) {
-	m.type = type; m.rows = rows; m.n = n; m.flags = 0; m.layout_units = 0;
+static int alloc_wmat(DevAlloc& da, WMat& m, int type, int rows, int n, int glu_half = 0) {
+	m.type = type; m.rows = rows; m.n = n; m.flags = 0; m.layout_units = 0; m.layout_frag = 0; m.glu_half = 0;
 	TypeInfo tinfo;
 	type_info(type, &tinfo);
+	if (mma_supported(type) && n % 32 == 0 && rows % MMA_RC == 0 && glu_half % 8 == 0 && tune("mma") && tune("tma") && !tune("mega") &&
+	    mma_smem_bytes(type, n, 2) <= 226 * 1024) {
+		// integer formats on the tensor-core path: fragment tiles (frag_layout.cuh); same byte count as on disk
+		m.layout_frag = 1;
+		m.glu_half = glu_half;
+		m.s0 = (size_t) n / 32 * frag_record_bytes(type); m.s1 = m.s2 = 0;
+		uint8_t* p = nullptr;
+		XALM_TRY(da.alloc((void**) &p, m.s0 * (rows / MMA_RC)));
+		m.p0 = p; m.p1 = m.p2 = nullptr;
+		return XALM_OK;
+	}
 	if (tinfo.block > 1 && unit_bytes(type) && n % 256 == 0 && rows % 8 == 0 && tune("tma")) {
 		// block formats on the TMA path: unit-interleaved rows (matvec_tma.cuh); same byte count as planar
 		m.layout_units = 1;
@@ -735,7 +794,8 @@ static int upload_piece(WMat& m, int dst_row, int type, const uint8_t* host, int
 	uint8_t* p0 = const_cast<uint8_t*>(m.p0) + (size_t) dst_row * m.s0;
 	uint8_t* p1 = m.p1 ? const_cast<uint8_t*>(m.p1) + (size_t) dst_row * m.s1 : nullptr;
 	uint8_t* p2 = m.p2 ? const_cast<uint8_t*>(m.p2) + (size_t) dst_row * m.s2 : nullptr;
-	if (m.layout_units) repack_units_kernel<<<1024, 256, 0, s>>>(type, st.p, width, rows, n, p0, m.s0);
+	if (m.layout_frag) repack_frag_kernel<<<1024, 256, 0, s>>>(type, st.p, width, dst_row, rows, m.rows, n, m.glu_half, const_cast<uint8_t*>(m.p0));
+	else if (m.layout_units) repack_units_kernel<<<1024, 256, 0, s>>>(type, st.p, width, rows, n, p0, m.s0);
 	else repack_kernel<<<1024, 256, 0, s>>>(type, st.p, width, rows, n, p0, m.s0, p1, m.s1, p2, m.s2);
 	XALM_CUDA_CHECK(cudaGetLastError());
 	if (type == XALM_F8_E4M3 || type == XALM_F8_E5M2) {
@@ -1173,12 +1233,12 @@ static int upload_impl(xalm_cuda_model* m, const char* name, int type_id, const 
 	}
 	if (type_id == XALM_U8) return set_error(XALM_ERR_UNSUPPORTED, "matmul: unsupported data type: U8 (%s)", name);
 
-	auto ensure = [&](WSlot& slot, int rows, int n) -> int {
+	auto ensure = [&](WSlot& slot, int rows, int n, int glu_half = 0) -> int {
 		if (slot.allocated) {
 			if (slot.m.type != type_id) return set_error(XALM_ERR_UNSUPPORTED, "%s: tensors fused into one matrix must share a type (%d vs %d)", name, type_id, slot.m.type);
 			return XALM_OK;
 		}
-		XALM_TRY(alloc_wmat(m->da, slot.m, type_id, rows, n));
+		XALM_TRY(alloc_wmat(m->da, slot.m, type_id, rows, n, glu_half));
 		slot.total_rows = rows;
 		slot.allocated = true;
 		return XALM_OK;
@@ -1224,11 +1284,11 @@ static int upload_impl(xalm_cuda_model* m, const char* name, int type_id, const 
 			XALM_TRY(put(L.wo.m, 0, 0, c.dim, R * m->q_dim_l, (R + 1) * m->q_dim_l));
 			break;
 		case P_GATE:
-			XALM_TRY(ensure(L.w13, 2 * m->hidden_l, c.dim));
+			XALM_TRY(ensure(L.w13, 2 * m->hidden_l, c.dim, m->hidden_l));
 			XALM_TRY(put(L.w13.m, 0, R * m->hidden_l, (R + 1) * m->hidden_l, 0, c.dim));
 			break;
 		case P_UP:
-			XALM_TRY(ensure(L.w13, 2 * m->hidden_l, c.dim));
+			XALM_TRY(ensure(L.w13, 2 * m->hidden_l, c.dim, m->hidden_l));
 			XALM_TRY(put(L.w13.m, m->hidden_l, R * m->hidden_l, (R + 1) * m->hidden_l, 0, c.dim));
 			break;
 		case P_DOWN:
@@ -1413,6 +1473,14 @@ static int enqueue_token(xalm_cuda_model* m, int mode, cudaStream_t s, int* n_la
 			head(a_w2.w, &a_w13.pf_ptr, &a_w13.pf_bytes);
 			if (l + 1 < c.n_layers) head(m->layers[l + 1].wqkv.m, &a_w2.pf_ptr, &a_w2.pf_bytes);
 			else if (mode == XALM_OUTPUT_LOGITS) head(m->wcls.m, &a_w2.pf_ptr, &a_w2.pf_bytes);
+			// ... and with the rmsnorm weights the next norm-fused kernel asks for before its dependency wait
+			auto norm_bytes = [&](int type) { return (unsigned int) ((size_t) c.dim * (type == XALM_F32 ? 4 : 2)); };
+			a_wo.pf_norm_ptr = (const uint8_t*) L.rms_ffn; a_wo.pf_norm_bytes = norm_bytes(L.rms_ffn_type);
+			if (l + 1 < c.n_layers) {
+				a_w2.pf_norm_ptr = (const uint8_t*) m->layers[l + 1].rms_att; a_w2.pf_norm_bytes = norm_bytes(m->layers[l + 1].rms_att_type);
+			} else if (mode == XALM_OUTPUT_LOGITS) {
+				a_w2.pf_norm_ptr = (const uint8_t*) m->rms_final; a_w2.pf_norm_bytes = norm_bytes(m->rms_final_type);
+			}
 		}
 		{ // attention pre-norm + q,k,v + clip + rope + KV write (+ sinks)
 			XALM_TRY(launch_matvec(a_qkv, s, pdl));
@@ -1557,7 +1625,7 @@ int xalm_cuda_finalize(xalm_cuda_model* m) {
 	XALM_TRY(m->da.alloc((void**) &m->xl, (size_t) 2 * c.dim * sizeof(uint2)));
 	XALM_CUDA_CHECK(cudaMemset(m->xl, 0, (size_t) 2 * c.dim * sizeof(uint2)));
 	if (m->tp_size > 1 && m->peer_ready && tune("tp_fused")) {
-		auto takes = [&](const WMat& w, int n) { return (w.layout_units || tma_eligible(w, n)) && w.rows % 8 == 0 && n % 256 == 0; };
+		auto takes = [&](const WMat& w, int n) { return w.layout_frag || ((w.layout_units || tma_eligible(w, n)) && w.rows % 8 == 0 && n % 256 == 0); };
 		bool ok = takes(m->wcls.m, c.dim) && (size_t) c.dim * sizeof(float) <= 64 * 1024;
 		for (auto& L : m->layers)
 			ok = ok && takes(L.wqkv.m, c.dim) && takes(L.wo.m, m->q_dim_l) && takes(L.w13.m, c.dim) && takes(L.w2.m, m->hidden_l);
@@ -1920,7 +1988,7 @@ int xalm_cuda_ffn(float* xout, const float* x, const void* w1, const void* w2, c
 	// W1|W3 stacked along rows, exactly as the model path fuses gate|up
 	DevAlloc da;
 	WMat w13;
-	int rc = alloc_wmat(da, w13, type_id, 2 * hidden_dim, dim);
+	int rc = alloc_wmat(da, w13, type_id, 2 * hidden_dim, dim, hidden_dim);
 	for (void* p : da.ptrs) t.v.push_back(p);
 	XALM_TRY(rc);
 	Staging st;
@@ -2052,7 +2120,7 @@ int xalm_cuda_bench_matvec(int type_id, int n, int d, int epi, int with_norm, in
 	TypeInfo ti;
 	if (!type_info(type_id, &ti)) return set_error(XALM_ERR_INVALID, "invalid type: %d", type_id);
 	if (n % ti.block) return set_error(XALM_ERR_INVALID, "n %% block");
-	if (epi != EPI_STORE && epi != EPI_GLU) return set_error(XALM_ERR_INVALID, "bench epi must be 0 (store) or 2 (glu)");
+	if (epi != EPI_STORE && epi != EPI_GLU && epi != EPI_RESIDUAL) return set_error(XALM_ERR_INVALID, "bench epi must be 0 (store), 1 (residual) or 2 (glu)");
 	const int rows = epi == EPI_GLU ? 2 * d : d;
 	DevAlloc da;
 	std::vector<WMat> ws(n_buffers);
@@ -2064,7 +2132,7 @@ int xalm_cuda_bench_matvec(int type_id, int n, int d, int epi, int with_norm, in
 	int rc = XALM_OK;
 	Staging sg;
 	for (int b = 0; b < n_buffers && rc == XALM_OK; b++) {
-		rc = alloc_wmat(da, ws[b], type_id, rows, n);
+		rc = alloc_wmat(da, ws[b], type_id, rows, n, epi == EPI_GLU ? d : 0);
 		if (rc == XALM_OK) rc = upload_piece(ws[b], 0, type_id, host.data(), n, 0, rows, 0, n, sg, 0);
 	}
 	float *dx = nullptr, *dy = nullptr, *dg = nullptr;
