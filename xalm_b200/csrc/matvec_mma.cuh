@@ -36,13 +36,13 @@ constexpr int MMA_NT = MMA_NCW * 32;
 constexpr int MMA_MP = 2;   // activation groups a lane keeps in flight (8 elements each): one pass for n <= 8192
 
 // ---- activation image in shared memory: 3 limb planes (stride n + 16 bytes: the three planes a quarter-warp reads fall into
-//      different banks) + one 32-byte table entry per block: {c-init (l2'), c-init (l1'), dx, sum x} {c-init (l0'), 0, dx * 65536, 0}
+//      different banks) + one 64-byte table entry per block, 16 bytes per lane position: {c-init (l2'), c-init (l1'), dx, sum x} {c-init (l0'), 0, dx * 65536, 0} {0} {0}
 struct XmView {
 	uint8_t* q;
 	int4* tbl;
 	int ps; // plane stride
 };
-__host__ __device__ inline size_t xm_bytes(int n) { return ((size_t) 3 * (n + 16) + (size_t) (n / 32) * 32 + 127) / 128 * 128; }
+__host__ __device__ inline size_t xm_bytes(int n) { return ((size_t) 3 * (n + 16) + (size_t) (n / 32) * 64 + 127) / 128 * 128; }
 __device__ __forceinline__ XmView xm_view(uint8_t* base, int n) { return {base, reinterpret_cast<int4*>(base + (size_t) 3 * (n + 16)), n + 16}; }
 
 // eight consecutive elements per lane, the four lanes 4k .. 4k+3 of a warp share a block (call with all lanes of the warp)
@@ -87,15 +87,19 @@ __device__ __forceinline__ void xm_store_group8(const XmView& v, int grp, const 
 		const int S0 = (int) s0, S1 = (int) (u & 0xFFFFu), S2 = (int) (u >> 16);
 		const int tot = (S0 - 4096) * 65536 + S1 * 256 + S2; // sum of the block's X (the offsets removed)
 		const float sx = __int2float_rn(tot) * dx;
-		v.tbl[2 * (grp >> 2)] = make_int4(-BIAS * S2, -BIAS * S1, (int) __float_as_uint(dx), (int) __float_as_uint(sx));
-		v.tbl[2 * (grp >> 2) + 1] = make_int4(-BIAS * (S0 - 4096), 0, (int) __float_as_uint(dx * 65536.f), 0);
+		int4* e = v.tbl + 4 * (grp >> 2); // one entry per lane position tig (columns 2 tig, 2 tig + 1); positions 2, 3 hold the zero columns
+		e[0] = make_int4(-BIAS * S2, -BIAS * S1, (int) __float_as_uint(dx), (int) __float_as_uint(sx));
+		e[1] = make_int4(-BIAS * (S0 - 4096), 0, (int) __float_as_uint(dx * 65536.f), 0);
+		e[2] = make_int4(0, 0, 0, 0);
+		e[3] = make_int4(0, 0, 0, 0);
 	}
 }
 
-__device__ __forceinline__ void mma_u8(int (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-	asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-	             : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
-	             : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+// d = a * b + c with separate accumulator-in registers: the c-init values are used as they come from the table, no copies
+__device__ __forceinline__ void mma_u8(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1, int c0, int c1) {
+	asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%10,%11};"
+	             : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3])
+	             : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "r"(c0), "r"(c1));
 }
 
 // ---- weight side: the A fragment and the scales of one record -------------------------------------------------------------
@@ -185,7 +189,7 @@ __host__ __device__ inline size_t mma_smem_bytes(int type, int n, int NS) {
 	size_t s = xm_bytes(n);
 	s += (size_t) NS * MMA_SB * frag_record_bytes(type);
 	s += (size_t) mma_pb(NS) * MMA_NCW * MMA_RC * sizeof(float);
-	s += (2 * (size_t) NS + mma_pb(NS)) * sizeof(uint64_t);
+	s += (2 * (size_t) NS + 2 * mma_pb(NS)) * sizeof(uint64_t);
 	s += MMA_NCW * sizeof(float);
 	return s + 128;
 }
@@ -197,7 +201,7 @@ struct MmaArgs {
 };
 
 template <int TYPE, bool NORM>
-__global__ void __launch_bounds__((MMA_NCW + 1) * 32, 1) matvec_mma_kernel(const MmaArgs ta) {
+__global__ void __launch_bounds__((MMA_NCW + 2) * 32, 1) matvec_mma_kernel(const MmaArgs ta) {
 	using F = MmaFmt<TYPE>;
 	constexpr int RC = MMA_RC, SB = MMA_SB, NCW = MMA_NCW, NT = MMA_NT, RB = F::RB, MP = MMA_MP;
 	constexpr int STAGE = SB * RB;
@@ -214,6 +218,7 @@ __global__ void __launch_bounds__((MMA_NCW + 1) * 32, 1) matvec_mma_kernel(const
 	uint64_t* full = reinterpret_cast<uint64_t*>(s_red + NCW);
 	uint64_t* empty = full + NS;
 	uint64_t* pbar = empty + NS;
+	uint64_t* pfree = pbar + PB; // a partial-sum buffer has been read by the epilogue warp
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	if (threadIdx.x == 0) {
@@ -221,7 +226,10 @@ __global__ void __launch_bounds__((MMA_NCW + 1) * 32, 1) matvec_mma_kernel(const
 			mbar_init(&full[s], 1);
 			mbar_init(&empty[s], NCW);
 		}
-		for (int s = 0; s < PB; s++) mbar_init(&pbar[s], NCW);
+		for (int s = 0; s < PB; s++) {
+			mbar_init(&pbar[s], NCW);
+			mbar_init(&pfree[s], 1);
+		}
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
 	__syncthreads();
@@ -252,6 +260,60 @@ __global__ void __launch_bounds__((MMA_NCW + 1) * 32, 1) matvec_mma_kernel(const
 				const unsigned long long kvb = (unsigned long long) a.step->kv_len * a.kv_dim * sizeof(__half);
 				l2_prefetch_slice(reinterpret_cast<const uint8_t*>(a.k_cache), kvb, (int) blockIdx.x, (int) gridDim.x);
 				l2_prefetch_slice(reinterpret_cast<const uint8_t*>(a.v_cache), kvb, (int) blockIdx.x, (int) gridDim.x);
+			}
+		}
+		return;
+	}
+
+	if (warp == NCW + 1) {
+		// ===================== epilogue warp: K-slice sums -> rows -> epilogue.  The 16 multiplying warps never wait for each other's
+		// partial sums (with a rotating reducer among them, a third of all warp samples sat in that wait: profiles/r2_mma.md) ==========
+		pdl_wait();
+		float nscale = 1.f;
+		int pb = 0, pph = 0;
+		for (int tt = 0; tt < my_tiles; tt++) {
+			const int row0 = ((int) blockIdx.x + tt * (int) gridDim.x) * RC;
+			float xold = 0.f; // residual: fetch the old activation before the wait, so the epilogue does not sit on an L2 round trip
+			if (a.epi == EPI_RESIDUAL && lane < RC && row0 + lane < a.d) xold = a.out[row0 + lane];
+			mbar_wait(&pbar[pb], pph);
+			if (NORM && tt == 0) { // the sums of squares were complete before any warp multiplied a tile
+				float tot = 0.f;
+#pragma unroll
+				for (int i = 0; i < NCW; i++) tot += s_red[i];
+				nscale = 1.0f / sqrtf(tot / (float) n + a.norm_eps); // infer.cpp:229-232
+			}
+			float yv = 0.f;
+			if (lane < RC) {
+				const float* pt = part + pb * NCW * RC;
+#pragma unroll
+				for (int w = 0; w < NCW; w++) yv += pt[w * RC + lane];
+			}
+			__syncwarp();
+			if (lane == 0) mbar_arrive(&pfree[pb]);
+			if (++pb == PB) { pb = 0; pph ^= 1; }
+			if (NORM) yv *= nscale;
+			const float ynext = __shfl_down_sync(0xffffffffu, yv, 1);
+			if (a.epi == EPI_RESIDUAL) {
+				if (lane < RC && row0 + lane < a.d) a.out[row0 + lane] = xold + yv;
+			} else if (a.epi == EPI_STORE && a.n_push) { // tensor parallel: this rank's partial rows go to every rank (NVLink stores)
+				if (lane < RC && (lane & 1) == 0 && row0 + lane < a.d) {
+					const unsigned int seq = a.step->ar_base + (unsigned int) a.push_idx + 1u;
+					const uint4 w = make_uint4(__float_as_uint(yv), seq, __float_as_uint(ynext), seq);
+					for (int p = 0; p < a.n_push; p++) *reinterpret_cast<uint4*>(a.push_dst[p] + row0 + lane) = w;
+				}
+			} else if (lane < RC && (lane & 1) == 0 && a.epi != EPI_GLU) { // GLU below (partner rows RC/2 apart)
+				const float y2[2] = {yv, ynext};
+				epilogue<2>(a, row0 + lane, y2);
+			}
+			if (a.epi == EPI_GLU) {
+				const float ypart = __shfl_down_sync(0xffffffffu, yv, RC / 2); // W3 value for the W1 row in this lane
+				if (lane < RC / 2) {
+					const int o = row0 / 2 + lane;
+					if (o < a.d) {
+						const float gt = a.act == XALM_SILU ? act_silu(yv) : act_gelu(yv);
+						a.out[o] = gt * ypart;
+					}
+				}
 			}
 		}
 		return;
@@ -388,13 +450,6 @@ __global__ void __launch_bounds__((MMA_NCW + 1) * 32, 1) matvec_mma_kernel(const
 		}
 		cbar();
 	}
-	float nscale = 1.f; // 1/rms of the input (infer.cpp:229-232)
-	if (NORM) {
-		float tot = 0.f;
-#pragma unroll
-		for (int i = 0; i < NCW; i++) tot += s_red[i];
-		nscale = 1.0f / sqrtf(tot / (float) n + a.norm_eps);
-	}
 	if (tl >= 0) tl_begin(500 + a.epi); // timeline event: activations staged
 
 	// this lane's place in the mma fragments
@@ -409,32 +464,25 @@ __global__ void __launch_bounds__((MMA_NCW + 1) * 32, 1) matvec_mma_kernel(const
 	for (int tt = 0; tt < my_tiles; tt++) {
 		const int pb = pb_next, pph = pph_next;
 		if (++pb_next == PB) { pb_next = 0; pph_next ^= 1; }
-		const int row0 = ((int) blockIdx.x + tt * (int) gridDim.x) * RC;
-		const bool reducer = warp == (tt % NCW);
-		float xold = 0.f; // residual: the reducer warp fetches the old activation now, so its epilogue does not sit on an L2 round trip
-		if (a.epi == EPI_RESIDUAL && reducer && lane < RC && row0 + lane < a.d) xold = a.out[row0 + lane];
 		float y0 = 0.f, y1 = 0.f; // rows g and g + 8 of the tile, this lane's columns
 		for (int kr = 0; kr < kranges; kr++) {
 			const int b0 = kr * SB;
 			const int nbs = min(SB, nb - b0);
 			const uint8_t* st = ring + (size_t) slot * STAGE;
 			mbar_wait(&full[slot], phase);
-#pragma unroll 2
-			for (int j = warp; j < nbs; j += NCW) {
-				const uint8_t* rec = st + (size_t) j * RB;
-				const int gb = b0 + j;
+			// one record (16 rows x 32 elements): rec = its bytes, bq = this lane's limb bytes of the block, tq = its table entry
+			auto record = [&](const uint8_t* rec, const uint8_t* bq, const int4* tq) {
 				uint32_t A[4];
 				float d0, d1, m0 = 0.f, m1 = 0.f;
 				F::load(rec, lane, g, A, d0, d1, m0, m1);
 				uint32_t B0 = bdef, B1 = bdef;
 				if (lane < 12) {
-					B0 = *reinterpret_cast<const uint32_t*>(bp + (size_t) gb * 32);
-					B1 = *reinterpret_cast<const uint32_t*>(bp + (size_t) gb * 32 + 16);
+					B0 = *reinterpret_cast<const uint32_t*>(bq);
+					B1 = *reinterpret_cast<const uint32_t*>(bq + 16);
 				}
-				int4 tb = make_int4(0, 0, 0, 0);
-				if (tig < 2) tb = tp[2 * gb];
-				int c[4] = {tb.x, tb.y, tb.x, tb.y};
-				mma_u8(c, A, B0, B1);
+				const int4 tb = *tq;
+				int c[4];
+				mma_u8(c, A, B0, B1, tb.x, tb.y);
 				const int v0 = c[1] * vmul + c[0], v1 = c[3] * vmul + c[2];
 				const float dxl = __int_as_float(tb.z);
 				y0 = fmaf(__int2float_rn(v0), d0 * dxl, y0);
@@ -444,6 +492,15 @@ __global__ void __launch_bounds__((MMA_NCW + 1) * 32, 1) matvec_mma_kernel(const
 					y0 = fmaf(m0, sxl, y0);
 					y1 = fmaf(m1, sxl, y1);
 				}
+			};
+			if (nbs == SB) { // a full stage: this warp's four records sit at fixed offsets (every address = base + immediate)
+				const uint8_t* rec = st + (size_t) warp * RB;
+				const uint8_t* bq = bp + (size_t) (b0 + warp) * 32;
+				const int4* tq = tp + 4 * (b0 + warp);
+#pragma unroll
+				for (int i = 0; i < SB / NCW; i++) record(rec + (size_t) i * NCW * RB, bq + (size_t) i * NCW * 32, tq + i * NCW * 4);
+			} else {
+				for (int j = warp; j < nbs; j += NCW) record(st + (size_t) j * RB, bp + (size_t) (b0 + j) * 32, tp + 4 * (b0 + j));
 			}
 			__syncwarp();
 			if (lane == 0) mbar_arrive(&empty[slot]);
@@ -455,6 +512,7 @@ __global__ void __launch_bounds__((MMA_NCW + 1) * 32, 1) matvec_mma_kernel(const
 		y1 += __shfl_xor_sync(0xffffffffu, y1, 1);
 		y0 += __shfl_xor_sync(0xffffffffu, y0, 2);
 		y1 += __shfl_xor_sync(0xffffffffu, y1, 2);
+		if (tt >= PB) mbar_wait(&pfree[pb], pph ^ 1); // the epilogue warp has read what this buffer held PB tiles ago
 		if (tig == 0) {
 			float* pt = part + (pb * NCW + warp) * RC;
 			pt[g] = y0;
@@ -462,39 +520,6 @@ __global__ void __launch_bounds__((MMA_NCW + 1) * 32, 1) matvec_mma_kernel(const
 		}
 		__syncwarp();
 		if (lane == 0) mbar_arrive(&pbar[pb]); // (release: this warp's partial sums are visible to whoever completes the wait)
-		if (reducer) { // rotating reducer: lane i owns row i of the tile
-			mbar_wait(&pbar[pb], pph);
-			float yv = 0.f;
-			if (lane < RC) {
-				const float* pt = part + pb * NCW * RC;
-#pragma unroll
-				for (int w = 0; w < NCW; w++) yv += pt[w * RC + lane];
-			}
-			if (NORM) yv *= nscale;
-			const float ynext = __shfl_down_sync(0xffffffffu, yv, 1);
-			if (a.epi == EPI_RESIDUAL) {
-				if (lane < RC && row0 + lane < a.d) a.out[row0 + lane] = xold + yv;
-			} else if (a.epi == EPI_STORE && a.n_push) { // tensor parallel: this rank's partial rows go to every rank (NVLink stores)
-				if (lane < RC && (lane & 1) == 0 && row0 + lane < a.d) {
-					const unsigned int seq = a.step->ar_base + (unsigned int) a.push_idx + 1u;
-					const uint4 w = make_uint4(__float_as_uint(yv), seq, __float_as_uint(ynext), seq);
-					for (int p = 0; p < a.n_push; p++) *reinterpret_cast<uint4*>(a.push_dst[p] + row0 + lane) = w;
-				}
-			} else if (lane < RC && (lane & 1) == 0 && a.epi != EPI_GLU) { // GLU below (partner rows RC/2 apart)
-				const float y2[2] = {yv, ynext};
-				epilogue<2>(a, row0 + lane, y2);
-			}
-			if (a.epi == EPI_GLU) {
-				const float ypart = __shfl_down_sync(0xffffffffu, yv, RC / 2); // W3 value for the W1 row in this lane
-				if (lane < RC / 2) {
-					const int o = row0 / 2 + lane;
-					if (o < a.d) {
-						const float gt = a.act == XALM_SILU ? act_silu(yv) : act_gelu(yv);
-						a.out[o] = gt * ypart;
-					}
-				}
-			}
-		}
 	}
 	tl_mark(tl, 3);
 }

@@ -412,7 +412,7 @@ static cudaError_t launch_mma_inst(const MmaArgs& ta, size_t smem, cudaStream_t 
 	if (e != cudaSuccess) return e;
 	int grid = num_sms(); // persistent: one CTA per SM
 	if (grid > ta.n_tiles) grid = ta.n_tiles;
-	return launch_smem(kern, dim3(grid), dim3((MMA_NCW + 1) * 32), smem, s, pdl, ta);
+	return launch_smem(kern, dim3(grid), dim3((MMA_NCW + 2) * 32), smem, s, pdl, ta);
 }
 static int launch_matvec_mma(const MatvecArgs& a, cudaStream_t s, bool pdl) {
 	const int t = a.w.type;
