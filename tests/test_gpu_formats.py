@@ -94,6 +94,20 @@ def test_matvec_random_x_vs_oracle(t):
         assert np.max(np.abs(y - ref)) <= 2e-6 * scale + 1e-6, f"{t.name} {d}x{n}"
 
 
+@pytest.mark.parametrize("t", [T.Q8_0, T.Q4_0, T.Q4_1, T.Q5_0, T.Q5_1, T.Q8], ids=lambda t: t.name)
+def test_matvec_tensor_core_shapes_vs_oracle(t):
+    """The tensor-core matvec (matvec_mma.cuh) on shapes with more 16-row tiles than SMs (150 / 300 / 151), rows that are not a
+    multiple of a ring stage (33 and 129 block columns), and run-to-run bit identity."""
+    for d, n in [(2400, 1056), (4800, 2048), (2432, 4128)]:
+        raw = random_raw(t, d, n, seed=5)
+        x = np.random.default_rng(8).standard_normal(n).astype(np.float32)
+        y = capi.matmul(x, raw, t.id, n, d)
+        ref = oracle.matmul(x, raw, t.id, n, d, acc_mode=2)
+        scale = np.sqrt(n) * np.abs(oracle.dequant(t.id, raw[: t.nbytes(n)], n)).max()
+        assert np.max(np.abs(y - ref)) <= 2e-6 * scale + 1e-6, f"{t.name} {d}x{n}"
+        assert np.array_equal(bits(y), bits(capi.matmul(x, raw, t.id, n, d))), "not bit-reproducible run to run"
+
+
 def test_matvec_rejects_what_the_reference_rejects():
     x = np.zeros(64, np.float32)
     with pytest.raises(capi.XalmError) as e:

@@ -77,7 +77,7 @@ static std::map<std::string, int>& tuning() {
 	    {"tma_grid_even", 0}, // percent: shrink the persistent grid down to this fraction of the full one if that makes tiles % grid == 0
 	    {"tp_fused", 1},     // tensor parallel: fuse the two per-layer exchanges into the matvec kernels (push over NVLink + receive in the next prologue)
 	    {"idp_per_sm", 2},
-	    {"mma", 1},         // integer formats: fragment-tile layout + tensor-core (mma.sync int8) matvec (matvec_mma.cuh); 0 = unit layout + dp4a
+	    {"mma", 2},         // integer formats on the tensor-core matvec (fragment tiles + mma.sync int8, matvec_mma.cuh): 0 = never (unit layout + dp4a), 1 = all six, 2 = the 4/5-bit formats (measured: q4_0 1.68 vs 1.86 ms/token; q8_0 1.90 vs 1.86)
     {"idp_ng", 0},      // consumer groups per CTA of the integer-dot matvec: 0 = by format, 2 = one 17-warp CTA per SM, 1 = two 9-warp CTAs
 	    {"tail_prefetch_mb", 8}, // each decode kernel pulls this many MB of the NEXT kernel's first weights into L2 once its own loads are issued
 	    {"prefill_split", 3}, // batched prefill operand precision: 1 = fp16 x fp16 (fastest; logits drift ~4e-2 over 32 layers), 2 = hi+lo fp16
@@ -734,7 +734,8 @@ static int alloc_wmat(DevAlloc& da, WMat& m, int type, int rows, int n, int glu_
 	m.type = type; m.rows = rows; m.n = n; m.flags = 0; m.layout_units = 0; m.layout_frag = 0; m.glu_half = 0;
 	TypeInfo tinfo;
 	type_info(type, &tinfo);
-	if (mma_supported(type) && n % 32 == 0 && rows % MMA_RC == 0 && glu_half % 8 == 0 && tune("mma") && tune("tma") && !tune("mega") &&
+	const bool mma_on = tune("mma") == 1 || (tune("mma") == 2 && type != XALM_Q8_0 && type != XALM_Q8);
+	if (mma_supported(type) && n % 32 == 0 && rows % MMA_RC == 0 && glu_half % 8 == 0 && mma_on && tune("tma") && !tune("mega") &&
 	    mma_smem_bytes(type, n, 2) <= 226 * 1024) {
 		// integer formats on the tensor-core path: fragment tiles (frag_layout.cuh); same byte count as on disk
 		m.layout_frag = 1;
