@@ -579,21 +579,32 @@ def main():
     hidden_l = cfg["hidden_dim"] // world
     k_bytes = 2 * hidden_l * cfg["dim"] * wtype.bytes // wtype.block
     nbuf = max(2, int(np.ceil(600e6 / k_bytes)))
+    # which matvec the MODEL runs for this format and sharding (xalm_cuda.cu: alloc_wmat): the tensor-core kernel (matvec_mma.cuh) for the
+    # 4/5-bit formats and, under tensor parallelism, for the 8-bit ones; the dp4a kernel (matvec_idp.cuh) for 8-bit on one GPU
+    int_fmt = args.wtype in ("q8_0", "q8", "q4_0", "q4_1", "q5_0", "q5_1")
+    mma_mode = int(os.environ.get("XALM_MMA", "2"))
+    mma_kernel = int_fmt and (2 * hidden_l) % 16 == 0 and (mma_mode == 1 or (mma_mode == 2 and (world > 1 or args.wtype not in ("q8_0", "q8"))))
+    idp_kernel = int_fmt and not mma_kernel and cfg["dim"] % 256 == 0 and (2 * hidden_l) % 8 == 0
+    if mma_kernel:
+        capi.tune("mma", 1)      # the stand-alone timing takes the same kernel as the sharded model
     k_ms = capi.bench_matvec(wtype.id, cfg["dim"], hidden_l, nbuf, 200, epi=2, with_norm=True)
+    if mma_kernel:
+        capi.tune("mma", mma_mode)
     k_gbs = k_bytes / (k_ms / 1e3) / 1e9
-    idp_kernel = args.wtype in ("q8_0", "q8", "q4_0", "q4_1", "q5_0", "q5_1") and cfg["dim"] % 256 == 0 and (2 * hidden_l) % 8 == 0
+    kname = "matvec_mma_kernel" if mma_kernel else "matvec_idp_kernel" if idp_kernel else "matvec_tma_kernel"
     traffic = None
     prof = os.path.join(ROOT, "profiles", "kernel_traffic.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get(f"{args.shape}_{args.wtype}_w13_idp_tp{world}_bytes")   # null unless captured for this kernel AND shard
+            traffic = json.load(open(prof)).get(f"{args.shape}_{args.wtype}_w13_{kname}_tp{world}_bytes")   # null unless captured for this kernel AND shard
         except Exception:
             traffic = None
 
     line = {
         "metric": "decode_tokens_per_s", "value": tps, "unit": "tok/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f32 activations and accumulation; integer weight formats multiply in int8 (dp4a) against 3 x int8 block-floating activation limbs" if idp_kernel else "f32",
+        "dtype": ("f32 activations and accumulation; integer weight formats multiply in int8 (" + ("mma.sync m16n8k32 u8" if mma_kernel else "dp4a") +
+                  ") against 3 x int8 block-floating activation limbs") if (idp_kernel or mma_kernel) else "f32",
         "data": "synthetic", "config": workload_config(args, cfg),
         "e2e": {"value": e2e_tps, "unit": "tok/s", "h2d_bytes_per_step": 32, "d2h_bytes_per_step": cfg["vocab_size"] * 4,
                 "device_sampler": {"value": args.steps / e2e_dev_s, "unit": "tok/s", "d2h_bytes_per_step": 4,
@@ -601,8 +612,7 @@ def main():
         "gpu_launches": launches,
         "clocks": clocks.summary(),
         "roofline": {"bound": "hbm", "achieved": k_gbs, "peak": peak, "unit": "GB/s", "frac": k_gbs / peak, "traffic": traffic,
-                     "kernel": f"matvec_idp_kernel<{args.wtype}, norm> (norm + gate|up + GLU) {2 * hidden_l}x{cfg['dim']}" if idp_kernel else
-                               f"matvec_tma_kernel<{args.wtype}, norm> (norm + gate|up + GLU) {2 * hidden_l}x{cfg['dim']}", "bytes_per_launch": k_bytes,
+                     "kernel": f"{kname}<{args.wtype}, norm> (norm + gate|up + GLU) {2 * hidden_l}x{cfg['dim']}", "bytes_per_launch": k_bytes,
                      "ms_per_launch": k_ms, "peak_source": peak_src, "timing": "CUDA events around 200 back-to-back launches on rotating buffers > L2"},
         "step_roofline": {"bytes_per_step": step_bytes, "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
                           "frac_of_8000": step_gbs / 8000.0, "formula": "Model::active_bytes(pos) (model.cpp:12-35), mean over the timed positions"},

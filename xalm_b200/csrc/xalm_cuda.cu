@@ -77,7 +77,7 @@ static std::map<std::string, int>& tuning() {
 	    {"tma_grid_even", 0}, // percent: shrink the persistent grid down to this fraction of the full one if that makes tiles % grid == 0
 	    {"tp_fused", 1},     // tensor parallel: fuse the two per-layer exchanges into the matvec kernels (push over NVLink + receive in the next prologue)
 	    {"idp_per_sm", 2},
-	    {"mma", 2},         // integer formats on the tensor-core matvec (fragment tiles + mma.sync int8, matvec_mma.cuh): 0 = never (unit layout + dp4a), 1 = all six, 2 = the 4/5-bit formats (measured: q4_0 1.68 vs 1.86 ms/token; q8_0 1.90 vs 1.86)
+	    {"mma", 2},         // integer formats on the tensor-core matvec (fragment tiles + mma.sync int8, matvec_mma.cuh): 0 = never (unit layout + dp4a), 1 = all six, 2 = the 4/5-bit formats, and the 8-bit ones under tensor parallelism (measured on one GPU: q4_0 1.68 vs 1.86 ms/token; q8_0 1.90 vs 1.86)
     {"idp_ng", 0},      // consumer groups per CTA of the integer-dot matvec: 0 = by format, 2 = one 17-warp CTA per SM, 1 = two 9-warp CTAs
 	    {"tail_prefetch_mb", 8}, // each decode kernel pulls this many MB of the NEXT kernel's first weights into L2 once its own loads are issued
 	    {"prefill_split", 3}, // batched prefill operand precision: 1 = fp16 x fp16 (fastest; logits drift ~4e-2 over 32 layers), 2 = hi+lo fp16
@@ -730,11 +730,13 @@ struct WSlot {
 	bool allocated = false;
 };
 
-static int alloc_wmat(DevAlloc& da, WMat& m, int type, int rows, int n, int glu_half = 0) {
+static int alloc_wmat(DevAlloc& da, WMat& m, int type, int rows, int n, int glu_half = 0, bool sharded = false) {
 	m.type = type; m.rows = rows; m.n = n; m.flags = 0; m.layout_units = 0; m.layout_frag = 0; m.glu_half = 0;
 	TypeInfo tinfo;
 	type_info(type, &tinfo);
-	const bool mma_on = tune("mma") == 1 || (tune("mma") == 2 && type != XALM_Q8_0 && type != XALM_Q8);
+	// 2 (default): the 4/5-bit formats always; the 8-bit ones under tensor parallelism, where the per-rank rows are short (the dp4a kernel
+	// maps one 32-element block to a lane: rows of 512 elements keep 16 of its 256 lanes busy) — TP2 611 -> 637 tok/s
+	const bool mma_on = tune("mma") == 1 || (tune("mma") == 2 && (sharded || (type != XALM_Q8_0 && type != XALM_Q8)));
 	if (mma_supported(type) && n % 32 == 0 && rows % MMA_RC == 0 && glu_half % 8 == 0 && mma_on && tune("tma") && !tune("mega") &&
 	    mma_smem_bytes(type, n, 2) <= 226 * 1024) {
 		// integer formats on the tensor-core path: fragment tiles (frag_layout.cuh); same byte count as on disk
@@ -1239,7 +1241,7 @@ static int upload_impl(xalm_cuda_model* m, const char* name, int type_id, const 
 			if (slot.m.type != type_id) return set_error(XALM_ERR_UNSUPPORTED, "%s: tensors fused into one matrix must share a type (%d vs %d)", name, type_id, slot.m.type);
 			return XALM_OK;
 		}
-		XALM_TRY(alloc_wmat(m->da, slot.m, type_id, rows, n, glu_half));
+		XALM_TRY(alloc_wmat(m->da, slot.m, type_id, rows, n, glu_half, m->tp_size > 1));
 		slot.total_rows = rows;
 		slot.allocated = true;
 		return XALM_OK;
