@@ -5,10 +5,12 @@
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 // load this library.  Nothing under xalm_b200/ links, imports or calls it.
 //
-// Parity status: the reference ships no tests / golden vectors,
-// and its C++ does not compile on x86 (arm_neon.h, <print>), so the
-// forward-pass part of this oracle is "PARITY UNPINNED" by the reference's own
-// tests.  What *is* pinned (tests/test_oracle_*.py, tests/golden/):
+// Parity status: PINNED TO THE REFERENCE ITSELF.  The reference ships no tests / golden vectors, but
+// its own C++ forward pass (src/infer.cpp, model.cpp, tensor.cpp, sampler.cpp, tokenizer.cpp) compiles untouched behind
+// the NEON / <print> shims of oracle/ref_shim/ (recipe: oracle/Makefile.ref -> oracle/_ref/libxalm_ref.so, dev container
+// only).  tests/golden/ref_fwd_*.npz are logits, greedy tokens, sampler probabilities and KV-cache bits produced by that
+// library (generator: tests/golden/make_ref_forward.py); tests/test_reference_forward.py requires this restatement to
+// reproduce them, and compares it with the live library when it is present.  Also pinned (tests/test_oracle_*.py):
 //   * block-quant dequant  == /root/reference/quants.py  (bit-exact, golden vectors)
 //   * fp8 decode           == torch float8 casts except the NaN/Inf codes the
 //                             reference treats as finite (types.h:302-314)
