@@ -174,8 +174,11 @@ int xalm_cuda_rope(float* vec, int d, int head_dim, int pos, float theta, int ro
 int xalm_cuda_ffn(float* xout, const float* x, const void* w1, const void* w2, const void* w3, int type_id,
                   int hidden_dim, int dim, int act);
 
-/* Integer tuning knobs by name ("pdl", "graph", "attn_splits", "attn_min_split", "mv_cfg_rows", "prefill_split"); an XALM_<KEY>
- * environment variable overrides the stored value.  Takes effect for graphs captured afterwards. */
+/* Integer tuning knobs by name ("pdl", "graph", "attn_splits", "attn_min_split", "mv_cfg_rows", "prefill_split", "idp", "mma", "mega",
+ * "tail_prefetch_mb", ...); an XALM_<KEY> environment variable overrides the stored value.  Takes effect for graphs captured
+ * afterwards; "mma" (which matvec kernel and device layout the integer formats take: 0 = dp4a + unit layout, 1 = tensor-core mma +
+ * fragment tiles, 2 = default: mma for the 4/5-bit formats and, under tensor parallelism, the 8-bit ones) and "mega" are read when a
+ * matrix is uploaded. */
 int xalm_cuda_tune(const char* key, int value);
 
 /* In-kernel timeline (there is no nsys here): with out == NULL start recording up to n_records kernels; with out != NULL
